@@ -1,0 +1,32 @@
+"""Shared parity-case catalogue: (name, fastq bytes, dna_order, quality_order, plus_rep).
+dna_order = 3 * CLI -d level, quality_order = CLI -q level (src/DsrcOperator.h:74-90)."""
+import synth
+
+
+def small_cases():
+    c = []
+    ill_b = synth.illumina(600, seed=11, regime="binned")
+    ill_f = synth.illumina(500, seed=12, regime="full")
+    ion = synth.ion454(250, seed=5)
+    for d, q in [(0, 0), (3, 1), (6, 2), (9, 2), (0, 2), (6, 0), (3, 2), (9, 1)]:
+        c.append(("ill_binned_d%d_q%d" % (d, q), ill_b, d, q, 0))
+        c.append(("ill_full_d%d_q%d" % (d, q), ill_f, d, q, 0))
+    for d, q in [(3, 1), (6, 2), (9, 2), (9, 1)]:
+        c.append(("ion454_d%d_q%d" % (d, q), ion, d, q, 0))
+    ion_plain = synth.ion454(200, seed=6, iupac=False)
+    c.append(("ion454_plain_d0_q0", ion_plain, 0, 0, 0))
+    c.append(("ill_barcode_d6_q2", synth.illumina(400, seed=13, barcode_var=True), 6, 2, 0))
+    c.append(("ill_barcode_d0_q0", synth.illumina(400, seed=13, barcode_var=True), 0, 0, 0))
+    c.append(("ill_plusrep_d6_q2", synth.illumina(300, seed=14, plus_rep=True), 6, 2, 1))
+    c.append(("mixed_titles_d6_q2", synth.mixed_titles(300), 6, 2, 0))
+    c.append(("mixed_titles_d0_q0", synth.mixed_titles(300), 0, 0, 0))
+    c.append(("ill_notail_d0_q0", synth.illumina(300, seed=15, tail_frac=0.0, regime="full"), 0, 0, 0))
+    c.append(("ill_alltail_d0_q0", synth.illumina(300, seed=16, tail_frac=0.9, regime="full"), 0, 0, 0))
+    for n in (1, 2, 3, 5):
+        c.append(("tiny%d_d6_q2" % n, synth.illumina(n, seed=20 + n, regime="full"), 6, 2, 0))
+        c.append(("tiny%d_d0_q0" % n, synth.illumina(n, seed=20 + n, regime="full"), 0, 0, 0))
+    c.append(("ill_long_d6_q2", synth.illumina(3000, seed=17), 6, 2, 0))
+    c.append(("ill_startbig_d6_q2", synth.illumina(700, seed=18, start_index=99990), 6, 2, 0))
+    c.append(("q1_valuevar_d6_q2", synth.illumina(40, seed=2, small_field=True), 6, 2, 0))
+    c.append(("q1_valuevar_big_d0_q0", synth.illumina(900, seed=3, small_field=True), 0, 0, 0))
+    return c

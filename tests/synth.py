@@ -1,0 +1,108 @@
+"""Seeded synthetic FASTQ generators for the parity tests (numpy; small sizes).
+
+Shapes follow SURVEY.md 8(d): Illumina-like fixed-length reads with (i) a 4-level binned quality
+regime and (ii) a 41-level regime, and 454/Ion-like variable-length reads with restricted IUPAC codes
+(only N,R,W,S may survive into the DNA stream -- SURVEY 8-Q9).
+
+The large-scale generator used by bench.py lives in the product (dsrc_b200/csrc/synth.cuh); this
+one exists so tests can build awkward inputs (ragged lengths, mixed titles, CRLF, ...).
+"""
+import numpy as np
+
+BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _markov_quals(rng, n, length, levels, stay=0.85):
+    """sticky Markov chain over `levels` (array of phred values) -> (n, length) uint8 phred."""
+    k = len(levels)
+    state = rng.integers(0, k, size=n)
+    out = np.empty((n, length), dtype=np.uint8)
+    for j in range(length):
+        move = rng.random(n) > stay
+        step = rng.integers(-2, 3, size=n)
+        state = np.where(move, np.clip(state + step, 0, k - 1), state)
+        out[:, j] = levels[state]
+    return out
+
+
+def illumina(n_reads, length=150, seed=1234, regime="binned", n_rate=2e-3, tail_frac=0.10,
+             start_index=1, crlf=False, plus_rep=False, barcode_var=False, small_field=False):
+    rng = np.random.default_rng(seed)
+    if regime == "binned":
+        levels = np.array([2, 12, 23, 37], dtype=np.uint8)
+    else:
+        levels = np.arange(0, 41, dtype=np.uint8)
+    q = _markov_quals(rng, n_reads, length, levels)
+    seq = BASES[rng.integers(0, 4, size=(n_reads, length))]
+    # '#' tails
+    tails = rng.random(n_reads) < tail_frac
+    tl = rng.integers(1, 41, size=n_reads)
+    for i in np.nonzero(tails)[0]:
+        q[i, length - tl[i]:] = 2
+    # N with quality '#'
+    nmask = rng.random((n_reads, length)) < n_rate
+    seq = np.where(nmask, ord("N"), seq).astype(np.uint8)
+    q = np.where(nmask, 2, q).astype(np.uint8)
+    qual = (q + 33).astype(np.uint8)
+    lines = []
+    eol = b"\r\n" if crlf else b"\n"
+    x = rng.integers(1000, 32000, size=n_reads)
+    yinc = rng.integers(0, 7, size=n_reads)
+    y = 1000 + np.cumsum(yinc)
+    bcs = [b"ACGTACGT", b"ACGTACGA", b"TTGTACGT", b"ACGAACGT"]
+    for i in range(n_reads):
+        idx = start_index + i
+        lane = 1 + (idx >> 12) % 4
+        tile = 1101 + (idx >> 8) % 96
+        bc = bcs[int(x[i]) % 4] if barcode_var else bcs[0]
+        title = b"@SIM.%d A00123:45:HXXXXXXX:%d:%d:%d:%d 1:N:0:%s" % (idx, lane, tile, x[i], y[i], bc)
+        if small_field:  # few-valued, non-run-length field early in the title -> ValueVar + Huffman, hit by SURVEY 8-Q1
+            title = b"@S.%d." % (int(x[i]) % 37) + title[1:] + b" %d" % (int(x[i]) % 11)
+        lines.append(title + eol + seq[i].tobytes() + eol + (b"+" + title[1:] if plus_rep else b"+") + eol
+                     + qual[i].tobytes() + eol)
+    return b"".join(lines)
+
+
+def ion454(n_reads, seed=5, iupac=True):
+    """variable-length reads, ~45 distinct qualities decreasing along the read, titles with
+    key=value fields; ambiguity codes N (mostly q<7), R, W, S (q>=7)."""
+    rng = np.random.default_rng(seed)
+    lines = []
+    for i in range(n_reads):
+        L = int(np.clip(rng.normal(350, 90), 40, 600))
+        s = BASES[rng.integers(0, 4, size=L)].copy()
+        # homopolymer bias
+        rep = rng.random(L) < 0.3
+        for j in range(1, L):
+            if rep[j]:
+                s[j] = s[j - 1]
+        base = np.linspace(40, 8, L) + rng.normal(0, 4, L)
+        q = np.clip(base, 0, 44).astype(np.uint8)
+        if iupac:
+            amb = rng.random(L) < 0.004
+            for j in np.nonzero(amb)[0]:
+                c = rng.choice(list(b"NNNRWS"))
+                s[j] = c
+                if c == ord("N") and rng.random() < 0.8:
+                    q[j] = rng.integers(0, 7)
+                else:
+                    q[j] = max(int(q[j]), 7)
+        name = "".join(rng.choice(list("ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"), size=14))
+        title = ("@%s rank=%07d x=%d y=%d length=%d" % (name, i + 1, rng.integers(1, 4096), rng.integers(1, 4096), L)).encode()
+        lines.append(title + b"\n" + s.tobytes() + b"\n+\n" + (q + 33).astype(np.uint8).tobytes() + b"\n")
+    return b"".join(lines)
+
+
+def mixed_titles(n_reads, length=50, seed=3):
+    """titles whose field structure changes mid-block -> TagRawEncoder path (FLAG_MIXED_FIELD_FORMATTING)."""
+    rng = np.random.default_rng(seed)
+    lines = []
+    for i in range(n_reads):
+        s = BASES[rng.integers(0, 4, size=length)]
+        q = rng.integers(2, 41, size=length).astype(np.uint8) + 33
+        if i % 7 == 3:
+            title = b"@lonely%d" % i
+        else:
+            title = b"@read_%d/1" % i
+        lines.append(title + b"\n" + s.tobytes() + b"\n+\n" + q.tobytes() + b"\n")
+    return b"".join(lines)
