@@ -1,0 +1,380 @@
+// C ABI of dsrc_b200 (include/dsrc_b200.h): context, HBM layout, the CUDA-stream block scheduler.
+//
+// Replaces DsrcCompressor::Process / DsrcDecompressor::Process (src/DsrcWorker.cpp:30-108): instead of N CPU
+// threads each owning a BlockCompressor, the block queue is cut into batches; each batch is laid out in HBM
+// (dense per-batch arrays + persistent per-CTA arenas) and pushed through the per-block kernels on a stream.
+#include "../../include/dsrc_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DSRCGPU_E_CUDA; } } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_NUM };
+static const char* K_NAMES[K_NUM] = {"count_lines", "parse", "preprocess", "tags", "model_quality", "model_dna", "rc_encode",
+                                     "q0_quality", "d0_dna", "meta_sizes", "gather", "decode"};
+
+struct dsrcgpu_ctx {
+    int device = 0, sms = 148;
+    dsrcgpu_dataset_t ds{};
+    dsrcgpu_settings_t cs{};
+    u32 max_block = 0, max_inflight = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // batch-wide device buffers
+    DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
+    DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
+    // persistent per-CTA arenas
+    DevBuf elem_a, elem_b, tagpool, dec_arena;
+    u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0;
+    // pinned host staging
+    BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
+    // per-kernel timing
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
+    std::vector<cudaEvent_t> ev_pool;
+    float k_ms[K_NUM]; u32 k_launches[K_NUM];
+    bool profiling = true;
+};
+
+static cudaEvent_t get_event(dsrcgpu_ctx* ctx)
+{
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct KTimer {
+    dsrcgpu_ctx* ctx; int k; cudaEvent_t a = nullptr, b = nullptr;
+    KTimer(dsrcgpu_ctx* c, int kid) : ctx(c), k(kid)
+    {
+        ctx->k_launches[k]++;
+        if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+    }
+    ~KTimer() { if (ctx->profiling) { cudaEventRecord(b, ctx->stream); ctx->ev_used.push_back({k, {a, b}}); } }
+};
+static void collect_times(dsrcgpu_ctx* ctx)
+{
+    for (auto& u : ctx->ev_used) {
+        float ms = 0; cudaEventElapsedTime(&ms, u.second.first, u.second.second);
+        ctx->k_ms[u.first] += ms;
+        ctx->ev_pool.push_back(u.second.first); ctx->ev_pool.push_back(u.second.second);
+    }
+    ctx->ev_used.clear();
+}
+
+extern "C" const char* dsrcgpu_last_error(dsrcgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_dataset_t* dataset, const dsrcgpu_settings_t* settings,
+                              uint32_t max_block_bytes, uint32_t max_inflight_blocks)
+{
+    if (!out || !dataset || !settings) return DSRCGPU_E_ARG;
+    *out = nullptr;
+    if (dataset->color_space || settings->lossy || settings->calc_crc32 || settings->tag_preserve_flags) return DSRCGPU_E_ARG;
+    if (dataset->quality_offset < 33 || dataset->quality_offset > 64) return DSRCGPU_E_ARG;
+    if (settings->dna_order > 9 || settings->quality_order > 2) return DSRCGPU_E_ARG;
+    if (max_block_bytes < 64 || max_block_bytes > (1u << 30)) return DSRCGPU_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) return DSRCGPU_E_CUDA;   // no CPU fallback, by design
+    dsrcgpu_ctx* ctx = new dsrcgpu_ctx();
+    ctx->device = device; ctx->ds = *dataset; ctx->cs = *settings; ctx->max_block = max_block_bytes;
+    memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DSRCGPU_E_CUDA; }
+    cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DSRCGPU_E_CUDA; }
+    if (max_inflight_blocks == 0) {
+        u64 n = (1ull << 30) / max_block_bytes;          // ~1 GiB of FASTQ per batch
+        max_inflight_blocks = (u32)std::min<u64>(std::max<u64>(n, 1), 4096);
+    }
+    ctx->max_inflight = max_inflight_blocks;
+    // persistent CTAs: 4 per SM unless the sort arenas (2 x 8 B x block/2 entries each) would exceed ~16 GiB
+    ctx->model_stride = (u64)max_block_bytes / 2 + 64;
+    u64 per_cta = ctx->model_stride * 8 * 2;
+    u64 ctas = std::min<u64>((u64)ctx->sms * 4, std::max<u64>(1, (16ull << 30) / per_cta));
+    ctas = std::min<u64>(ctas, max_inflight_blocks);
+    ctx->model_ctas = (u32)ctas;
+    ctx->tag_ctas = (u32)std::min<u64>((u64)ctx->sms * 4, max_inflight_blocks);
+    *out = ctx;
+    return DSRCGPU_OK;
+}
+
+extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->in, &ctx->desc, &ctx->state, &ctx->result, &ctx->probe, &ctx->lines, &ctx->qcat, &ctx->dcat, &ctx->trip_q, &ctx->trip_d,
+                      &ctx->ftab, &ctx->streams, &ctx->out, &ctx->r_title_off, &ctx->r_seq_off, &ctx->r_qua_off, &ctx->r_title_len, &ctx->r_qua_len,
+                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_probe) cudaFreeHost(ctx->h_probe);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void dsrcgpu_set_profiling(dsrcgpu_ctx* ctx, int on) { if (ctx) ctx->profiling = on != 0; }
+extern "C" int dsrcgpu_last_kernel_times(dsrcgpu_ctx* ctx, const char** names, float* ms, uint32_t* launches, int max_entries)
+{
+    int n = 0;
+    for (int k = 0; k < K_NUM && n < max_entries; ++k) {
+        if (!ctx->k_launches[k]) continue;
+        if (names) names[n] = K_NAMES[k];
+        if (ms) ms[n] = ctx->k_ms[k];
+        if (launches) launches[n] = ctx->k_launches[k];
+        ++n;
+    }
+    return n;
+}
+
+static int ensure_host(dsrcgpu_ctx* ctx, u32 n)
+{
+    if (n <= ctx->h_cap) return DSRCGPU_OK;
+    if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_probe) cudaFreeHost(ctx->h_probe);
+    ctx->h_desc = nullptr; ctx->h_result = nullptr; ctx->h_probe = nullptr; ctx->h_cap = 0;
+    CK(cudaHostAlloc((void**)&ctx->h_desc, sizeof(BlockDesc) * n, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&ctx->h_result, sizeof(BlockResult) * n, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&ctx->h_probe, sizeof(BlockProbe) * n, cudaHostAllocDefault));
+    ctx->h_cap = n;
+    return DSRCGPU_OK;
+}
+
+static inline u64 align_up(u64 v, u64 a) { return (v + a - 1) / a * a; }
+
+static int status_to_error(dsrcgpu_ctx* ctx, u32 status, u32 blk)
+{
+    char msg[160];
+    int code = DSRCGPU_E_MALFORMED;
+    const char* what = "malformed FASTQ block";
+    if (status & 0x100) { code = DSRCGPU_E_CAPACITY; what = "output buffer too small"; }
+    else if (status == ST_UNSUPPORTED) { code = DSRCGPU_E_UNSUPPORTED; what = "block outside the supported envelope (see DESIGN.md limits)"; }
+    else if (status == ST_OVERFLOW) { code = DSRCGPU_E_UNSUPPORTED; what = "internal stream arena too small for this block"; }
+    snprintf(msg, sizeof(msg), "block %u: %s (status %u)", blk, what, status);
+    ctx->err = msg;
+    return code;
+}
+
+// one batch of blocks through the encode pipeline. d_in/d_out are device pointers.
+static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, const u32* blk_len, const u32* blk_tagcap, u32 n,
+                        u8* d_out, u64 out_base, u64 out_cap, u64* out_end)
+{
+    int rc = ensure_host(ctx, n);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->desc.ensure(sizeof(BlockDesc) * n));
+    CK(ctx->state.ensure(sizeof(BlockState) * n));
+    CK(ctx->result.ensure(sizeof(BlockResult) * n));
+    CK(ctx->probe.ensure(sizeof(BlockProbe) * n));
+    BlockDesc* hd = ctx->h_desc;
+    for (u32 i = 0; i < n; ++i) {
+        memset(&hd[i], 0, sizeof(BlockDesc));
+        hd[i].in_off = in_off[i]; hd[i].in_len = blk_len[i];
+        hd[i].tag_cap = blk_tagcap ? blk_tagcap[i] : 0xFFFFFFFFu;
+        if (blk_len[i] == 0 || blk_len[i] > ctx->max_block) { ctx->err = "block length 0 or above max_block_bytes"; return DSRCGPU_E_ARG; }
+    }
+    Workspace ws{};
+    ws.in = d_in; ws.desc = (const BlockDesc*)ctx->desc.p; ws.state = (BlockState*)ctx->state.p;
+    ws.result = (BlockResult*)ctx->result.p; ws.probe = (BlockProbe*)ctx->probe.p;
+    ws.n_blocks = n; ws.qoff = ctx->ds.quality_offset; ws.plus_rep = ctx->ds.plus_repetition;
+    ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order;
+    ws.out = d_out; ws.out_cap = out_cap;
+
+    // pass 1: count lines / fields so the batch can be laid out exactly
+    CK(cudaMemcpyAsync(ctx->desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    { KTimer t(ctx, K_COUNT); launch_count_lines(ws, s); }
+    CK(cudaMemcpyAsync(ctx->h_probe, ctx->probe.p, sizeof(BlockProbe) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+
+    u64 lines = 0, recs = 0, syms = 0, ftab = 0, streams = 0;
+    for (u32 i = 0; i < n; ++i) {
+        BlockDesc& d = hd[i];
+        const u32 nl = ctx->h_probe[i].n_lines;
+        d.line_base = (u32)lines; d.line_cap = nl; lines += nl;
+        d.rec_base = (u32)recs; d.rec_cap = nl / 4 + 1; recs += d.rec_cap;
+        d.sym_base = syms; d.sym_cap = d.in_len / 2 + 16; syms += align_up(d.sym_cap, 16);
+        d.n_fields = ctx->h_probe[i].n_fields;
+        d.ftab_base = ftab; ftab += (u64)d.n_fields * d.rec_cap;
+        d.stream_base = streams;
+        d.stream_cap[0] = 64;
+        d.stream_cap[1] = (u32)align_up((u64)d.in_len / 2 + (128u << 10), 16);
+        d.stream_cap[2] = (u32)align_up((u64)d.in_len / 2 * 3 + 256, 16);
+        d.stream_cap[3] = (u32)align_up((u64)d.in_len / 2 * 3 + (256u << 10), 16);
+        streams += (u64)d.stream_cap[0] + d.stream_cap[1] + d.stream_cap[2] + d.stream_cap[3];
+        if (lines >= (1ull << 32) || recs >= (1ull << 32)) { ctx->err = "batch too large"; return DSRCGPU_E_ARG; }
+    }
+    CK(ctx->lines.ensure(lines * 4));
+    CK(ctx->r_title_off.ensure(recs * 4)); CK(ctx->r_seq_off.ensure(recs * 4)); CK(ctx->r_qua_off.ensure(recs * 4));
+    CK(ctx->r_qcat_off.ensure(recs * 4)); CK(ctx->r_dcat_off.ensure(recs * 4));
+    CK(ctx->r_title_len.ensure(recs * 2)); CK(ctx->r_qua_len.ensure(recs * 2)); CK(ctx->r_dna_len.ensure(recs * 2)); CK(ctx->r_trunc_len.ensure(recs * 2));
+    CK(ctx->qcat.ensure(syms)); CK(ctx->dcat.ensure(syms));
+    const bool rc_q = ctx->cs.quality_order > 0, rc_d = ctx->cs.dna_order > 0;
+    if (rc_q) CK(ctx->trip_q.ensure(syms * 8));
+    if (rc_d) CK(ctx->trip_d.ensure(syms * 8));
+    CK(ctx->ftab.ensure(ftab * 8));
+    CK(ctx->streams.ensure(streams));
+    if (rc_q || rc_d) { CK(ctx->elem_a.ensure(ctx->model_stride * 8 * ctx->model_ctas)); CK(ctx->elem_b.ensure(ctx->model_stride * 8 * ctx->model_ctas)); }
+    CK(ctx->tagpool.ensure(tagpool_bytes_per_block() * ctx->tag_ctas));
+
+    ws.lines = (u32*)ctx->lines.p;
+    ws.rec.title_off = (u32*)ctx->r_title_off.p; ws.rec.seq_off = (u32*)ctx->r_seq_off.p; ws.rec.qua_off = (u32*)ctx->r_qua_off.p;
+    ws.rec.title_len = (u16*)ctx->r_title_len.p; ws.rec.qua_len = (u16*)ctx->r_qua_len.p; ws.rec.dna_len = (u16*)ctx->r_dna_len.p;
+    ws.rec.trunc_len = (u16*)ctx->r_trunc_len.p; ws.rec.qcat_off = (u32*)ctx->r_qcat_off.p; ws.rec.dcat_off = (u32*)ctx->r_dcat_off.p;
+    ws.qcat = (u8*)ctx->qcat.p; ws.dcat = (u8*)ctx->dcat.p;
+    ws.trip_q = (u64*)ctx->trip_q.p; ws.trip_d = (u64*)ctx->trip_d.p;
+    ws.elem_a = (u64*)ctx->elem_a.p; ws.elem_b = (u64*)ctx->elem_b.p;
+    ws.ftab = (u64*)ctx->ftab.p; ws.streams = (u8*)ctx->streams.p;
+    ws.tagpool = (u8*)ctx->tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
+
+    CK(cudaMemcpyAsync(ctx->desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    { KTimer t(ctx, K_PARSE); launch_parse(ws, s); }
+    { KTimer t(ctx, K_PREP); launch_preprocess(ws, s); }
+    { KTimer t(ctx, K_TAGS); launch_tags(ws, s, ctx->tag_ctas); }
+    if (rc_q) { KTimer t(ctx, K_MODEL_Q); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
+    else { KTimer t(ctx, K_Q0); launch_q0_quality(ws, s); }
+    if (rc_d) { KTimer t(ctx, K_MODEL_D); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
+    else { KTimer t(ctx, K_D0); launch_d0_dna(ws, s); }
+    if (rc_q || rc_d) { KTimer t(ctx, K_RC); launch_rc_encode(ws, s); }
+    { KTimer t(ctx, K_SIZES); launch_meta_and_sizes(ws, s, out_base); }
+    { KTimer t(ctx, K_GATHER); launch_gather(ws, s); }
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    collect_times(ctx);
+    u64 end = out_base;
+    for (u32 i = 0; i < n; ++i) {
+        if (ctx->h_result[i].status != ST_OK) return status_to_error(ctx, ctx->h_result[i].status, i);
+        end = ctx->h_result[i].out_off + ctx->h_result[i].total_size;
+    }
+    *out_end = end;
+    return DSRCGPU_OK;
+}
+
+static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const u64* blk_off, const u32* blk_len, const u32* blk_tagcap, u32 n,
+                       u8* out, u64 out_cap, u32* out_sizes, u64* raw_sizes, u64* comp_sizes)
+{
+    if (!ctx) return DSRCGPU_E_ARG;
+    if (!fastq || !blk_off || !blk_len || !out || !out_sizes) { ctx->err = "null argument"; return DSRCGPU_E_ARG; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return DSRCGPU_E_CUDA; }
+    memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
+    u64 out_pos = 0;
+    std::vector<u64> offs;
+    for (u32 first = 0; first < n;) {
+        u32 cnt = std::min(ctx->max_inflight, n - first);
+        const u8* d_in; u8* d_out; u64 batch_out_base, batch_out_cap;
+        offs.resize(cnt);
+        if (on_device) {
+            d_in = fastq;
+            for (u32 i = 0; i < cnt; ++i) offs[i] = blk_off[first + i];
+            d_out = out; batch_out_base = out_pos; batch_out_cap = out_cap;
+        } else {
+            // stage the batch: one copy when the blocks are a (near-)contiguous ascending span, packed copies otherwise
+            u64 lo = blk_off[first], hi = 0, sum = 0; bool asc = true;
+            for (u32 i = 0; i < cnt; ++i) {
+                u64 o = blk_off[first + i]; u32 l = blk_len[first + i];
+                if (i && o < blk_off[first + i - 1] + blk_len[first + i - 1]) asc = false;
+                lo = std::min(lo, o); hi = std::max(hi, o + l); sum += l;
+            }
+            if (asc && hi - lo <= sum + (u64)cnt * 64) {
+                CK(ctx->in.ensure(hi - lo + 16));
+                CK(cudaMemcpyAsync(ctx->in.p, fastq + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+                for (u32 i = 0; i < cnt; ++i) offs[i] = blk_off[first + i] - lo;
+            } else {
+                CK(ctx->in.ensure(sum + (u64)cnt * 16 + 16));
+                u64 p = 0;
+                for (u32 i = 0; i < cnt; ++i) {
+                    CK(cudaMemcpyAsync((u8*)ctx->in.p + p, fastq + blk_off[first + i], blk_len[first + i], cudaMemcpyHostToDevice, ctx->stream));
+                    offs[i] = p; p += align_up(blk_len[first + i], 16);
+                }
+            }
+            d_in = (const u8*)ctx->in.p;
+            u64 bound = 0;
+            for (u32 i = 0; i < cnt; ++i) bound += (u64)blk_len[first + i] + (blk_len[first + i] >> 1) + 4096;   // generous: DSRC never expands by 1.5x
+            bound = std::min(bound, out_cap - out_pos + 1);
+            CK(ctx->out.ensure(bound));
+            d_out = (u8*)ctx->out.p; batch_out_base = 0; batch_out_cap = std::min<u64>(bound, out_cap - out_pos);
+        }
+        u64 end = 0;
+        int rc = encode_batch(ctx, d_in, offs.data(), blk_len + first, blk_tagcap ? blk_tagcap + first : nullptr, cnt,
+                              d_out, batch_out_base, batch_out_cap, &end);
+        if (rc) return rc;
+        for (u32 i = 0; i < cnt; ++i) {
+            const BlockResult& r = ctx->h_result[i];
+            out_sizes[first + i] = r.total_size;
+            if (raw_sizes) for (int k = 0; k < 4; ++k) raw_sizes[(u64)(first + i) * 4 + k] = r.raw[k];
+            if (comp_sizes) for (int k = 0; k < 4; ++k) comp_sizes[(u64)(first + i) * 4 + k] = r.stream_size[k];
+        }
+        if (on_device) out_pos = end;
+        else {
+            CK(cudaMemcpyAsync(out + out_pos, d_out, end, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            out_pos += end;
+        }
+        first += cnt;
+    }
+    return DSRCGPU_OK;
+}
+
+extern "C" int dsrcgpu_encode_blocks(dsrcgpu_ctx* ctx, const uint8_t* fastq, const uint64_t* blk_off, const uint32_t* blk_len,
+                                     const uint32_t* blk_tagcap, uint32_t n, uint8_t* out, uint64_t out_cap,
+                                     uint32_t* out_sizes, uint64_t* raw_stream_sizes, uint64_t* comp_stream_sizes)
+{
+    return encode_impl(ctx, fastq, false, blk_off, blk_len, blk_tagcap, n, out, out_cap, out_sizes, raw_stream_sizes, comp_stream_sizes);
+}
+extern "C" int dsrcgpu_encode_blocks_device(dsrcgpu_ctx* ctx, const uint8_t* d_fastq, const uint64_t* blk_off, const uint32_t* blk_len,
+                                            const uint32_t* blk_tagcap, uint32_t n, uint8_t* d_out, uint64_t out_cap,
+                                            uint32_t* out_sizes, uint64_t* raw_stream_sizes, uint64_t* comp_stream_sizes)
+{
+    return encode_impl(ctx, d_fastq, true, blk_off, blk_len, blk_tagcap, n, d_out, out_cap, out_sizes, raw_stream_sizes, comp_stream_sizes);
+}
+
+// ---- Q1 helpers (pure host) ----
+extern "C" uint32_t dsrcgpu_tag_field_count(const uint8_t* t, uint32_t len)
+{
+    u32 nf = 1;
+    for (u32 i = 0; i < len; ++i) {
+        u8 c = t[i];
+        nf += (c == ' ' || c == '.' || c == '_' || c == ',' || c == '=' || c == ':' || c == '/' || c == '-' || c == '#' || c == 0);
+    }
+    return nf;
+}
+extern "C" uint32_t dsrcgpu_tag_capacity_after(uint32_t cap, uint32_t n_fields)
+{
+    for (u32 k = 0; k < n_fields; ++k) if (k == cap) cap = cap ? cap * 2 : 1;
+    return cap;
+}
+
+// ---- memory helpers ----
+extern "C" int dsrcgpu_device_alloc(dsrcgpu_ctx* ctx, uint64_t bytes, void** p) { cudaSetDevice(ctx->device); CK(cudaMalloc(p, bytes)); return DSRCGPU_OK; }
+extern "C" int dsrcgpu_device_free(dsrcgpu_ctx* ctx, void* p) { cudaSetDevice(ctx->device); CK(cudaFree(p)); return DSRCGPU_OK; }
+extern "C" int dsrcgpu_memcpy_h2d(dsrcgpu_ctx* ctx, void* d, const void* h, uint64_t bytes)
+{
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return DSRCGPU_OK;
+}
+extern "C" int dsrcgpu_memcpy_d2h(dsrcgpu_ctx* ctx, void* h, const void* d, uint64_t bytes)
+{
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return DSRCGPU_OK;
+}
+extern "C" int dsrcgpu_host_alloc(uint64_t bytes, void** p) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? DSRCGPU_OK : DSRCGPU_E_NOMEM; }
+extern "C" int dsrcgpu_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? DSRCGPU_OK : DSRCGPU_E_CUDA; }

@@ -1,0 +1,18 @@
+// host-side launchers of the per-block kernels (each .cu defines its own)
+#pragma once
+#include "common.cuh"
+
+void launch_count_lines(const Workspace& ws, cudaStream_t s);
+void launch_parse(const Workspace& ws, cudaStream_t s);
+void launch_preprocess(const Workspace& ws, cudaStream_t s);
+void launch_tags(const Workspace& ws, cudaStream_t s, u32 ctas);   // ctas = number of TagPool arenas
+// order-k contexts -> (freq,cum,tot) triples; ctas = persistent CTAs owning a sort arena of `stride` entries each
+void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
+void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
+void launch_rc_encode(const Workspace& ws, cudaStream_t s);       // serial range-coder chains, one thread per (block, stream)
+void launch_q0_quality(const Workspace& ws, cudaStream_t s);      // -q0: positional / truncated / RLE Huffman
+void launch_d0_dna(const Workspace& ws, cudaStream_t s);          // -d0: 2-bit pack / Huffman
+void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base);  // StoreMetaData + dense output offsets (first block at out_base)
+void launch_gather(const Workspace& ws, cudaStream_t s);          // meta|tags|quality|dna -> dense output
+
+u64 tagpool_bytes_per_block();

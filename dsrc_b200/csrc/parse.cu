@@ -1,0 +1,264 @@
+// Block parsing and record preprocessing kernels (one CTA owns one block).
+//   k_count_lines : counts line terminators per block so the host can size the record arrays exactly
+//   k_parse       : FastqParser::ParseFrom / ReadNextRecord / SkipLine   (src/FastqParser.cpp:140-164, FastqParser.h:40-115)
+//   k_preprocess  : LosslessRecordsProcessor::ProcessForward + Initialize/FinalizeStats
+//                   (src/RecordsProcessor.cpp:104-133, 180-267) and BlockCompressor::AnalyzeMetaData
+//                   (src/BlockCompressor.cpp:184-205), re-expressed as scans + warp ballots:
+//                   the reference compacts in place; we emit two dense per-block symbol arrays
+//                   (qcat: processed quality bytes, dcat: retained DNA indices) that every later
+//                   kernel indexes with coalesced accesses.
+#include "common.cuh"
+#include "kernels.h"
+
+// a byte terminates a line iff it is '\r', or '\n' not directly after '\r' (SkipLine: CR LF counts once)
+__device__ __forceinline__ bool is_term(const u8* b, u32 p)
+{
+    u8 c = b[p];
+    return c == '\r' || (c == '\n' && !(p > 0 && b[p - 1] == '\r'));
+}
+
+__global__ void __launch_bounds__(DSRC_CTA) k_count_lines(Workspace ws)
+{
+    const BlockDesc& d = ws.desc[blockIdx.x];
+    const u8* b = ws.in + d.in_off;
+    u32 cnt = 0;
+    for (u32 p = threadIdx.x; p < d.in_len; p += DSRC_CTA) cnt += is_term(b, p);
+    cnt = warp_red_sum(cnt);
+    __shared__ u32 sm[DSRC_WARPS];
+    if (lane_id() == 0) sm[warp_id()] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int w = 0; w < DSRC_WARPS; ++w) t += sm[w];
+        BlockState& st = ws.state[blockIdx.x];
+        st.n_lines = t + 1;     // the last line has no terminator (the chunk is cut before its final '\n')
+        st.status = ST_OK;
+        // field count of the first title (TagAnalyzer::InitializeFieldsStats, src/TagModeler.cpp:159-224): sizes the field table
+        u32 nf = 0, i = 0;
+        for (; i < d.in_len && b[i] != '\n' && b[i] != '\r'; ++i) {
+            u8 c = b[i];
+            nf += (c == ' ' || c == '.' || c == '_' || c == ',' || c == '=' || c == ':' || c == '/' || c == '-' || c == '#' || c == 0);
+        }
+        ws.probe[blockIdx.x].n_lines = t + 1;
+        ws.probe[blockIdx.x].n_fields = nf + 1;
+    }
+}
+
+__global__ void __launch_bounds__(DSRC_CTA) k_parse(Workspace ws)
+{
+    const BlockDesc& d = ws.desc[blockIdx.x];
+    BlockState& st = ws.state[blockIdx.x];
+    const u8* b = ws.in + d.in_off;
+    u32* lines = ws.lines + d.line_base;
+    __shared__ u32 sm[DSRC_WARPS + 1];
+    __shared__ u32 s_carry, s_skipped, s_bad;
+    __shared__ unsigned long long s_raw[3];
+    if (threadIdx.x == 0) { s_carry = 0; s_skipped = 0; s_bad = 0xFFFFFFFFu; s_raw[0] = s_raw[1] = s_raw[2] = 0; }
+    __syncthreads();
+    // phase A: positions of all terminators, in order. lines[k] = position | (CRLF ? 1<<31 : 0)
+    u32 skipped = 0;
+    for (u32 base = 0; base < d.in_len; base += DSRC_CTA) {
+        u32 p = base + threadIdx.x;
+        bool t = p < d.in_len && is_term(b, p);
+        u32 total, ex = block_excl_sum(t ? 1u : 0u, sm, &total);
+        u32 carry = s_carry;
+        if (t) {
+            bool crlf = b[p] == '\r' && p + 1 < d.in_len && b[p + 1] == '\n';
+            skipped += crlf;
+            u32 k = carry + ex;
+            if (k < d.line_cap) lines[k] = p | (crlf ? 0x80000000u : 0u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    skipped = warp_red_sum(skipped);
+    if (lane_id() == 0 && skipped) atomicAdd(&s_skipped, skipped);
+    __syncthreads();
+    const u32 n_term = s_carry;
+    // the final line ends at in_len unless the chunk ends with a terminator
+    u32 last_end = n_term ? ((lines[n_term - 1] & 0x7FFFFFFFu) + 1 + (lines[n_term - 1] >> 31)) : 0;
+    u32 n_lines = n_term + (last_end < d.in_len ? 1 : 0);
+    u32 n_rec = n_lines / 4;
+    if (n_lines % 4 != 0 || n_rec == 0 || n_rec > d.rec_cap) {   // the reference would silently drop the tail record
+        if (threadIdx.x == 0) { st.status = ST_MALFORMED; st.n_rec = 0; }
+        return;
+    }
+    // phase B: one thread per record
+    const RecArrays& R = ws.rec;
+    unsigned long long rt = 0, rs = 0, rq = 0;
+    for (u32 r = threadIdx.x; r < n_rec; r += DSRC_CTA) {
+        u32 e[4], s[4];
+        for (int l = 0; l < 4; ++l) {
+            u32 k = 4 * r + l;
+            u32 prev = k ? lines[k - 1] : 0;
+            s[l] = k ? ((prev & 0x7FFFFFFFu) + 1 + (prev >> 31)) : 0;
+            e[l] = k < n_term ? (lines[k] & 0x7FFFFFFFu) : d.in_len;
+        }
+        u32 tl = e[0] - s[0], sl = e[1] - s[1], pl = e[2] - s[2], ql = e[3] - s[3];
+        bool ok = tl > 0 && tl <= 65535 && b[s[0]] == '@' && pl > 0 && sl == ql && sl <= 65535;
+        if (!ok) atomicMin(&s_bad, r);
+        u32 g = d.rec_base + r;
+        R.title_off[g] = s[0]; R.title_len[g] = (u16)tl;
+        R.seq_off[g] = s[1]; R.qua_off[g] = s[3]; R.qua_len[g] = (u16)ql;
+        rt += tl; rs += sl; rq += ql;
+    }
+    for (int o = 16; o; o >>= 1) {
+        rt += __shfl_xor_sync(0xFFFFFFFFu, rt, o); rs += __shfl_xor_sync(0xFFFFFFFFu, rs, o); rq += __shfl_xor_sync(0xFFFFFFFFu, rq, o);
+    }
+    if (lane_id() == 0) { atomicAdd(&s_raw[0], rt); atomicAdd(&s_raw[1], rs); atomicAdd(&s_raw[2], rq); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_bad != 0xFFFFFFFFu) { st.status = ST_MALFORMED; st.n_rec = 0; return; }
+        st.n_rec = n_rec;
+        st.chunk_size = d.in_len - s_skipped;
+        st.raw[0] = 0; st.raw[1] = s_raw[0]; st.raw[2] = s_raw[1]; st.raw[3] = s_raw[2];
+    }
+}
+
+// dnaToIndexTable (src/RecordsProcessor.cpp:185-205): A0 G1 C2 T3 N4 R5 W6 S7 K8 M9 D10 V11 H12 B13 Y14 X15 U16 .17 -18
+__device__ __forceinline__ u32 dna_index(u8 c)
+{
+    switch (c) {
+    case 'A': return 0; case 'G': return 1; case 'C': return 2; case 'T': return 3; case 'N': return 4;
+    case 'R': return 5; case 'W': return 6; case 'S': return 7; case 'K': return 8; case 'M': return 9;
+    case 'D': return 10; case 'V': return 11; case 'H': return 12; case 'B': return 13; case 'Y': return 14;
+    case 'X': return 15; case 'U': return 16; case '.': return 17; case '-': return 18;
+    default: return 255;
+    }
+}
+
+__global__ void __launch_bounds__(DSRC_CTA) k_preprocess(Workspace ws)
+{
+    const BlockDesc& d = ws.desc[blockIdx.x];
+    BlockState& st = ws.state[blockIdx.x];
+    if (st.status != ST_OK) return;
+    const u8* b = ws.in + d.in_off;
+    const RecArrays& R = ws.rec;
+    const u32 n_rec = st.n_rec, rb = d.rec_base;
+    u8* qcat = ws.qcat + d.sym_base;
+    u8* dcat = ws.dcat + d.sym_base;
+
+    __shared__ u32 sm[DSRC_WARPS + 1];
+    __shared__ u32 s_carry;
+    __shared__ u32 s_qf[DSRC_WARPS][256];
+    __shared__ u32 s_df[DSRC_WARPS][20];
+    __shared__ u32 s_min, s_max, s_th, s_rle, s_bad;
+    for (u32 i = threadIdx.x; i < DSRC_WARPS * 256; i += DSRC_CTA) (&s_qf[0][0])[i] = 0;
+    for (u32 i = threadIdx.x; i < DSRC_WARPS * 20; i += DSRC_CTA) (&s_df[0][0])[i] = 0;
+    if (threadIdx.x == 0) { s_carry = 0; s_min = 0xFFFFFFFFu; s_max = 0; s_th = 0; s_rle = 0; s_bad = 0; }
+    __syncthreads();
+
+    // A: exclusive prefix of quality lengths -> qcat offsets
+    for (u32 base = 0; base < n_rec; base += DSRC_CTA) {
+        u32 r = base + threadIdx.x;
+        u32 len = r < n_rec ? R.qua_len[rb + r] : 0;
+        u32 total, ex = block_excl_sum(len, sm, &total);
+        u32 carry = s_carry;
+        if (r < n_rec) R.qcat_off[rb + r] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    const u32 q_total = s_carry;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = 0;
+    if (q_total > d.sym_cap) { if (threadIdx.x == 0) st.status = ST_OVERFLOW; return; }
+
+    // B: one warp per record: LUT, offset removal, ambiguity transfer, statistics
+    const u32 w = warp_id(), ln = lane_id();
+    u32 mn = 0xFFFFFFFFu, mx = 0, th_sum = 0, rle_sum = 0, bad = 0;
+    for (u32 r = w; r < n_rec; r += DSRC_WARPS) {
+        const u32 len = R.qua_len[rb + r];
+        const u8* seq = b + R.seq_off[rb + r];
+        const u8* qua = b + R.qua_off[rb + r];
+        u8* qo = qcat + R.qcat_off[rb + r];
+        u32 kept = 0, th = 0, rle = 0; u32 last_q = 255;
+        for (u32 j0 = 0; j0 < len; j0 += 32) {
+            u32 j = j0 + ln; bool in = j < len;
+            u32 s = in ? dna_index(seq[j]) : 0;
+            u32 q = in ? (u8)(qua[j] - ws.qoff) : 0;
+            bool moved = in && s > 3 && q < 7;                    // RecordsProcessor.cpp:228-233
+            if (moved) q = (u8)(q + (128 + ((s - 3 + 1) << 3) - 16));
+            bool keep = in && !moved;
+            if (in && s == 255) bad = 1;                         // not a DNA symbol the reference knows
+            if (in) { qo[j] = (u8)q; atomicAdd(&s_qf[w][q], 1u); }
+            if (keep && s < 20) atomicAdd(&s_df[w][s], 1u);
+            kept += __popc(__ballot_sync(0xFFFFFFFFu, keep));
+            u32 pq = __shfl_up_sync(0xFFFFFFFFu, q, 1);
+            if (ln == 0) pq = last_q;
+            rle += __popc(__ballot_sync(0xFFFFFFFFu, in && q != pq));
+            u32 not2 = __ballot_sync(0xFFFFFFFFu, in && q != 2);
+            if (not2) th = j0 + 31 - __clz(not2);
+            u32 cnt_in = min(32u, len - j0);
+            last_q = __shfl_sync(0xFFFFFFFFu, q, cnt_in - 1);
+        }
+        if (len > 0 && last_q == 2 && rle > 0) rle -= 1;          // :259-260 (per record; the block counter is > 0 whenever it matters)
+        if (ln == 0) { R.dna_len[rb + r] = (u16)kept; R.trunc_len[rb + r] = (u16)(th + (len > 0)); }
+        mn = min(mn, len); mx = max(mx, len); th_sum += th; rle_sum += rle;
+    }
+    if (ln == 0) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); atomicAdd(&s_th, th_sum); atomicAdd(&s_rle, rle_sum); if (bad) s_bad = 1; }
+    if (bad && ln != 0) s_bad = 1;
+    __syncthreads();
+
+    // C: exclusive prefix of retained-base counts -> dcat offsets
+    for (u32 base = 0; base < n_rec; base += DSRC_CTA) {
+        u32 r = base + threadIdx.x;
+        u32 len = r < n_rec ? R.dna_len[rb + r] : 0;
+        u32 total, ex = block_excl_sum(len, sm, &total);
+        u32 carry = s_carry;
+        if (r < n_rec) R.dcat_off[rb + r] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    const u32 d_total = s_carry;
+
+    // D: compaction of the retained bases (ballot prefix inside the warp)
+    for (u32 r = w; r < n_rec; r += DSRC_WARPS) {
+        const u32 len = R.qua_len[rb + r];
+        const u8* seq = b + R.seq_off[rb + r];
+        const u8* qua = b + R.qua_off[rb + r];
+        u8* dout = dcat + R.dcat_off[rb + r];
+        u32 base = 0;
+        for (u32 j0 = 0; j0 < len; j0 += 32) {
+            u32 j = j0 + ln; bool in = j < len;
+            u32 s = in ? dna_index(seq[j]) : 0;
+            u32 q = in ? (u8)(qua[j] - ws.qoff) : 0;
+            bool keep = in && !(s > 3 && q < 7);
+            u32 m = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) dout[base + __popc(m & ((1u << ln) - 1))] = (u8)s;
+            base += __popc(m);
+        }
+    }
+    __syncthreads();
+
+    // E: FinalizeStats (dense symbol ranks) + AnalyzeMetaData
+    if (threadIdx.x < 256) {
+        u32 f = 0;
+        for (int k = 0; k < DSRC_WARPS; ++k) f += s_qf[k][threadIdx.x];
+        st.qfreq[threadIdx.x] = f;
+        s_qf[0][threadIdx.x] = f;
+    }
+    if (threadIdx.x < 20) {
+        u32 f = 0;
+        for (int k = 0; k < DSRC_WARPS; ++k) f += s_df[k][threadIdx.x];
+        st.dfreq[threadIdx.x] = f;
+        s_df[0][threadIdx.x] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 qc = 0, dc = 0;
+        for (u32 i = 0; i < 256; ++i) st.qrank[i] = s_qf[0][i] ? (u8)qc++ : (u8)255;
+        for (u32 i = 0; i < 20; ++i) st.drank[i] = s_df[0][i] ? (u8)dc++ : (u8)255;
+        st.q_count = qc; st.d_count = dc;
+        st.q_total = q_total; st.d_total = d_total;
+        st.min_len = s_min; st.max_len = s_max; st.raw_len = q_total; st.th_len = s_th; st.rle_len = s_rle;
+        st.flags = (s_min != s_max) ? 2u : 0u;
+        if (s_bad) st.status = ST_UNSUPPORTED;
+    }
+}
+
+void launch_count_lines(const Workspace& ws, cudaStream_t s) { k_count_lines<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }
+void launch_parse(const Workspace& ws, cudaStream_t s) { k_parse<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }
+void launch_preprocess(const Workspace& ws, cudaStream_t s) { k_preprocess<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }
