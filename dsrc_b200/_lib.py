@@ -69,5 +69,11 @@ def lib():
     L.dsrcgpu_host_free.argtypes = [vp]
     L.dsrcgpu_synth_fastq_device.restype = C.c_int
     L.dsrcgpu_synth_fastq_device.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
+    L.dsrcgpu_synth_fastq_host.restype = C.c_int
+    L.dsrcgpu_synth_fastq_host.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
+    L.dsrcgpu_cut_blocks.restype = C.c_uint64
+    L.dsrcgpu_cut_blocks.argtypes = [vp, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64]
+    L.dsrcgpu_last_call_ms.restype = C.c_float
+    L.dsrcgpu_last_call_ms.argtypes = [vp]
     _lib = L
     return L

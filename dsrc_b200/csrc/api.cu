@@ -44,14 +44,15 @@ struct dsrcgpu_ctx {
     DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
     DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
     // persistent per-CTA arenas
-    DevBuf elem_a, elem_b, tagpool, dec_arena;
-    u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0;
+    DevBuf elem_a, elem_b, tagpool, dec_arena, q0_arena;
+    u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0; u32 q0_ctas = 0; u64 q0_stride = 0;
     // pinned host staging
     BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
     // per-kernel timing
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
     std::vector<cudaEvent_t> ev_pool;
     float k_ms[K_NUM]; u32 k_launches[K_NUM];
+    cudaEvent_t call_a = nullptr, call_b = nullptr; float call_ms = 0;
     bool profiling = true;
 };
 
@@ -110,6 +111,8 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     ctas = std::min<u64>(ctas, max_inflight_blocks);
     ctx->model_ctas = (u32)ctas;
     ctx->tag_ctas = (u32)std::min<u64>((u64)ctx->sms * 4, max_inflight_blocks);
+    ctx->q0_stride = q0_arena_bytes(max_block_bytes);
+    ctx->q0_ctas = (u32)std::min<u64>(std::min<u64>((u64)ctx->sms * 2, max_inflight_blocks), std::max<u64>(1, (16ull << 30) / ctx->q0_stride));
     *out = ctx;
     return DSRCGPU_OK;
 }
@@ -121,7 +124,7 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->in, &ctx->desc, &ctx->state, &ctx->result, &ctx->probe, &ctx->lines, &ctx->qcat, &ctx->dcat, &ctx->trip_q, &ctx->trip_d,
                       &ctx->ftab, &ctx->streams, &ctx->out, &ctx->r_title_off, &ctx->r_seq_off, &ctx->r_qua_off, &ctx->r_title_len, &ctx->r_qua_len,
-                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena};
+                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena, &ctx->q0_arena};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -234,6 +237,7 @@ static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, con
     CK(ctx->streams.ensure(streams));
     if (rc_q || rc_d) { CK(ctx->elem_a.ensure(ctx->model_stride * 8 * ctx->model_ctas)); CK(ctx->elem_b.ensure(ctx->model_stride * 8 * ctx->model_ctas)); }
     CK(ctx->tagpool.ensure(tagpool_bytes_per_block() * ctx->tag_ctas));
+    if (!rc_q || !rc_d) CK(ctx->q0_arena.ensure(ctx->q0_stride * ctx->q0_ctas));
 
     ws.lines = (u32*)ctx->lines.p;
     ws.rec.title_off = (u32*)ctx->r_title_off.p; ws.rec.seq_off = (u32*)ctx->r_seq_off.p; ws.rec.qua_off = (u32*)ctx->r_qua_off.p;
@@ -250,9 +254,9 @@ static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, con
     { KTimer t(ctx, K_PREP); launch_preprocess(ws, s); }
     { KTimer t(ctx, K_TAGS); launch_tags(ws, s, ctx->tag_ctas); }
     if (rc_q) { KTimer t(ctx, K_MODEL_Q); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
-    else { KTimer t(ctx, K_Q0); launch_q0_quality(ws, s); }
+    else { KTimer t(ctx, K_Q0); launch_q0_quality(ws, s, (u8*)ctx->q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
     if (rc_d) { KTimer t(ctx, K_MODEL_D); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
-    else { KTimer t(ctx, K_D0); launch_d0_dna(ws, s); }
+    else { KTimer t(ctx, K_D0); launch_d0_dna(ws, s, (u8*)ctx->q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
     if (rc_q || rc_d) { KTimer t(ctx, K_RC); launch_rc_encode(ws, s); }
     { KTimer t(ctx, K_SIZES); launch_meta_and_sizes(ws, s, out_base); }
     { KTimer t(ctx, K_GATHER); launch_gather(ws, s); }
@@ -276,6 +280,8 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     if (!fastq || !blk_off || !blk_len || !out || !out_sizes) { ctx->err = "null argument"; return DSRCGPU_E_ARG; }
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return DSRCGPU_E_CUDA; }
     memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
+    if (!ctx->call_a) { cudaEventCreate(&ctx->call_a); cudaEventCreate(&ctx->call_b); }
+    cudaEventRecord(ctx->call_a, ctx->stream);
     u64 out_pos = 0;
     std::vector<u64> offs;
     for (u32 first = 0; first < n;) {
@@ -331,7 +337,42 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         }
         first += cnt;
     }
+    cudaEventRecord(ctx->call_b, ctx->stream);
+    CK(cudaEventSynchronize(ctx->call_b));
+    cudaEventElapsedTime(&ctx->call_ms, ctx->call_a, ctx->call_b);
     return DSRCGPU_OK;
+}
+
+extern "C" float dsrcgpu_last_call_ms(dsrcgpu_ctx* ctx) { return ctx ? ctx->call_ms : 0.f; }
+
+// IFastqStreamReader::ReadNextChunk + GetNextRecordPos (src/FastqStream.cpp:18-98) over an in-memory file: the block
+// queue the reference's reader thread would produce for a chunk buffer of `cbuf` bytes (CLI: -b MB << 20).
+static void cut_skip_eol(const u8* d, u64& p, u64 size, bool& crlf)
+{
+    while (p < size && d[p] != '\n' && d[p] != '\r') ++p;
+    if (p + 1 < size && d[p] == '\r' && d[p + 1] == '\n') { crlf = true; ++p; }
+}
+extern "C" uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks)
+{
+    u64 start = 0, nb = 0; bool crlf = false;
+    if (cbuf <= 8192) return 0;
+    while (start < size) {
+        const u64 avail = size - start;
+        u64 blk, adv;
+        if (avail >= cbuf) {
+            // the window is full: resume 8 KiB before its end, cut at the next line that starts a record
+            const u8* w = data + start; u64 p = cbuf - 8192;
+            cut_skip_eol(w, p, cbuf, crlf); ++p;
+            while (p < cbuf && w[p] != '@') { cut_skip_eol(w, p, cbuf, crlf); ++p; }
+            u64 cand = p;
+            cut_skip_eol(w, p, cbuf, crlf); ++p;
+            if (p < cbuf && w[p] == '@') cand = p;      // the first '@' line was a quality string
+            adv = cand; blk = cand - 1 - (crlf ? 1 : 0);
+        } else { adv = avail; blk = avail - 1 - (crlf ? 1 : 0); }
+        if (nb < max_blocks && off && len) { off[nb] = start; len[nb] = (u32)blk; }
+        ++nb; start += adv;
+    }
+    return nb;
 }
 
 extern "C" int dsrcgpu_encode_blocks(dsrcgpu_ctx* ctx, const uint8_t* fastq, const uint64_t* blk_off, const uint32_t* blk_len,

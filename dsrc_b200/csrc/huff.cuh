@@ -33,7 +33,7 @@ __device__ __forceinline__ u64 huf_warp_argmin(const HufWork* w, u32 cnt)
 // Builds codes for `n_in` symbols with frequencies freq[]. All lanes of the calling warp must participate.
 // code[]/len[] receive the n leaf codes; ser receives the StoreTree serialisation; returns its size in bytes
 // (0xFFFFFFFF on overflow of ser_cap).
-__device__ u32 huf_build_warp(const u32* freq, u32 n_in, HufWork* w, u32* code, u8* len, u8* ser, u32 ser_cap)
+static __device__ u32 huf_build_warp(const u32* freq, u32 n_in, HufWork* w, u32* code, u8* len, u8* ser, u32 ser_cap)
 {
     const u32 ln = lane_id();
     u32 n = n_in < 2 ? 2 : n_in;                      // huffman.cpp:101

@@ -10,8 +10,10 @@ void launch_tags(const Workspace& ws, cudaStream_t s, u32 ctas);   // ctas = num
 void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
 void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
 void launch_rc_encode(const Workspace& ws, cudaStream_t s);       // serial range-coder chains, one thread per (block, stream)
-void launch_q0_quality(const Workspace& ws, cudaStream_t s);      // -q0: positional / truncated / RLE Huffman
-void launch_d0_dna(const Workspace& ws, cudaStream_t s);          // -d0: 2-bit pack / Huffman
+// -q0: positional / truncated / RLE Huffman; -d0: 2-bit pack / Huffman. arena: ctas x stride bytes of per-CTA scratch
+void launch_q0_quality(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u32 ctas);
+void launch_d0_dna(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u32 ctas);
+u64 q0_arena_bytes(u64 max_block_bytes);
 void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base);  // StoreMetaData + dense output offsets (first block at out_base)
 void launch_gather(const Workspace& ws, cudaStream_t s);          // meta|tags|quality|dna -> dense output
 

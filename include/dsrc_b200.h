@@ -96,6 +96,14 @@ int dsrcgpu_decode_blocks_device(dsrcgpu_ctx* ctx, const uint8_t* d_dsrc, const 
 uint32_t dsrcgpu_tag_field_count(const uint8_t* title, uint32_t title_len);
 uint32_t dsrcgpu_tag_capacity_after(uint32_t capacity_before, uint32_t n_fields);
 
+/* == IFastqStreamReader::ReadNextChunk + GetNextRecordPos (src/FastqStream.cpp:18-98) over an in-memory FASTQ file:
+ * fills off[]/len[] with the chunks the reference's reader hands to Store for a chunk buffer of cbuf bytes
+ * (CLI: -b MB << 20). Pure host function. Returns the number of blocks (only the first max_blocks are stored). */
+uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks);
+
+/* device-timed duration (ms, CUDA events on the context's stream) of the last encode/decode call */
+float dsrcgpu_last_call_ms(dsrcgpu_ctx* ctx);
+
 /* Measurement support: device time (ms, CUDA events on the context's streams) spent in each kernel family during
  * the last encode/decode call, and launch counts. names[i] are static strings. Returns the number of entries. */
 int dsrcgpu_last_kernel_times(dsrcgpu_ctx* ctx, const char** names, float* ms, uint32_t* launches, int max_entries);
@@ -115,6 +123,9 @@ int dsrcgpu_host_free(void* h_ptr);
  * returns bytes written in *bytes. profile: 0 Illumina 4-level binned, 1 Illumina 41-level, 2 454/Ion variable. */
 int dsrcgpu_synth_fastq_device(dsrcgpu_ctx* ctx, uint32_t profile, uint64_t seed, uint64_t first_read, uint64_t n_reads,
                                uint8_t* d_out, uint64_t out_cap, uint64_t* bytes);
+/* CPU twin producing the same bytes into host memory (tests; hosts that want the data without a device round trip) */
+int dsrcgpu_synth_fastq_host(uint32_t profile, uint64_t seed, uint64_t first_read, uint64_t n_reads,
+                             uint8_t* out, uint64_t out_cap, uint64_t* bytes);
 
 #ifdef __cplusplus
 }
