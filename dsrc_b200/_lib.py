@@ -55,6 +55,8 @@ def lib():
     L.dsrcgpu_last_kernel_times.restype = C.c_int
     L.dsrcgpu_last_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), u32p, C.c_int]
     L.dsrcgpu_set_profiling.argtypes = [vp, C.c_int]
+    L.dsrcgpu_phase_cycles.restype = C.c_int
+    L.dsrcgpu_phase_cycles.argtypes = [vp, u64p, C.c_int]
     L.dsrcgpu_device_alloc.restype = C.c_int
     L.dsrcgpu_device_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.dsrcgpu_device_free.restype = C.c_int

@@ -44,7 +44,8 @@ struct dsrcgpu_ctx {
     DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
     DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
     // persistent per-CTA arenas
-    DevBuf elem_a, elem_b, tagpool, dec_arena, q0_arena;
+    DevBuf elem_a, elem_b, tagpool, dec_arena, q0_arena, prof;
+    bool phase_prof = false;
     u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0; u32 q0_ctas = 0; u64 q0_stride = 0;
     // pinned host staging
     BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
@@ -124,7 +125,7 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->in, &ctx->desc, &ctx->state, &ctx->result, &ctx->probe, &ctx->lines, &ctx->qcat, &ctx->dcat, &ctx->trip_q, &ctx->trip_d,
                       &ctx->ftab, &ctx->streams, &ctx->out, &ctx->r_title_off, &ctx->r_seq_off, &ctx->r_qua_off, &ctx->r_title_len, &ctx->r_qua_len,
-                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena, &ctx->q0_arena};
+                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena, &ctx->q0_arena, &ctx->prof};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -134,7 +135,17 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
     delete ctx;
 }
 
-extern "C" void dsrcgpu_set_profiling(dsrcgpu_ctx* ctx, int on) { if (ctx) ctx->profiling = on != 0; }
+extern "C" void dsrcgpu_set_profiling(dsrcgpu_ctx* ctx, int on) { if (ctx) { ctx->profiling = (on & 1) != 0; ctx->phase_prof = (on & 2) != 0; } }
+extern "C" int dsrcgpu_phase_cycles(dsrcgpu_ctx* ctx, uint64_t* out64, int reset)
+{
+    if (!ctx || !out64) return DSRCGPU_E_ARG;
+    memset(out64, 0, 64 * 8);
+    if (!ctx->prof.p) return DSRCGPU_OK;
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpy(out64, ctx->prof.p, 64 * 8, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(ctx->prof.p, 0, 64 * 8));
+    return DSRCGPU_OK;
+}
 extern "C" int dsrcgpu_last_kernel_times(dsrcgpu_ctx* ctx, const char** names, float* ms, uint32_t* launches, int max_entries)
 {
     int n = 0;
@@ -201,6 +212,7 @@ static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, con
     ws.n_blocks = n; ws.qoff = ctx->ds.quality_offset; ws.plus_rep = ctx->ds.plus_repetition;
     ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order;
     ws.out = d_out; ws.out_cap = out_cap;
+    if (ctx->phase_prof) { if (!ctx->prof.p) { CK(ctx->prof.ensure(64 * 8)); CK(cudaMemsetAsync(ctx->prof.p, 0, 64 * 8, s)); } ws.prof = (u64*)ctx->prof.p; }
 
     // pass 1: count lines / fields so the batch can be laid out exactly
     CK(cudaMemcpyAsync(ctx->desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));

@@ -58,6 +58,9 @@ __device__ void dna_cfg(u32 order, u32 scheme, ModelCfg& c)
     c.key_bits = c.ord * c.bits; c.sym_order = 0; c.rescale = 0;
 }
 
+#define LONG_T 48                              // context runs longer than this are walked by a whole warp
+#define LONGQ_MAX 2048
+
 struct ModelShared {
     union {
         struct {
@@ -67,11 +70,16 @@ struct ModelShared {
             u32 hist[2][256];
         } s;
         u16 cnt[CNT_BYTES / 2];
+        struct { u32 B[DSRC_WARPS][128]; u32 P[DSRC_WARPS][128]; } l;   // per-warp row state of the long-run walker
     } u;
+    u32 longq[LONGQ_MAX];
+    u32 n_long;
     u8 rank[256];
     ModelCfg cfg;
     u32 M, ok;
 };
+
+#define PROF_MARK(slot) do { if (ws.prof && threadIdx.x == 0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&ws.prof[slot], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
 
 __device__ __forceinline__ void hist_add(u32* hist, u32 digit, bool active)
 {
@@ -142,47 +150,128 @@ __device__ void sort_pass(ModelShared& S, const u64* src, u64* dst, u32 M, u32 s
     __syncthreads();
 }
 
+#define TRIP(f, cum, tot) ((u64)(f) | ((u64)(cum) << 16) | ((u64)(tot) << 32))
+
+// A whole warp walks ONE long context run starting at sorted[a], 32 symbols per step. Within a row of 32 symbols of the
+// same context the adaptive row seen by lane l is the row at the start of the row plus 2 x (the symbols of the lanes
+// before l), so freq / cum / tot come from ballots and popcounts; the halving rescale of TSymbolCoderRC::Rescale
+// (src/SymbolCoderRC.h:69-73) can only fire once per ~32 K symbols of a context: a row that could contain it is
+// replayed symbol by symbol by lane 0.
+__device__ void warp_run(ModelShared& S, const u64* sorted, u64* trip, u32 M, u32 a)
+{
+    const u32 N = S.cfg.alpha, limit = (1u << 16) - 2 * N, ln = lane_id(), lt = (1u << ln) - 1;
+    u32* B = S.u.l.B[warp_id()]; u32* P = S.u.l.P[warp_id()];
+    for (u32 s = ln; s < N; s += 32) B[s] = 1;
+    u32 T = N;
+    const u64 key = sorted[a] >> 40;
+    __syncwarp();
+    for (u32 row = a;; row += 32) {
+        const u32 i = row + ln;
+        const u64 e = i < M ? sorted[i] : ~0ull;
+        const bool valid = (e >> 40) == key;
+        const u32 vm = __ballot_sync(0xFFFFFFFFu, valid);
+        if (!vm) break;
+        const u32 nv = __popc(vm);
+        const u32 sym = (u32)(e >> 32) & 255u;
+        if (T + 2 * (nv - 1) >= limit) {
+            if (ln == 0) {
+                for (u32 j = 0; j < nv; ++j) {
+                    const u64 ej = sorted[row + j]; const u32 s = (u32)(ej >> 32) & 255u;
+                    if (T >= limit) { T = 0; for (u32 q = 0; q < N; ++q) { u32 c = B[q]; c -= c >> 1; B[q] = c; T += c; } }
+                    const u32 f = B[s]; u32 cum = 0;
+                    for (u32 q = 0; q < s; ++q) cum += B[q];
+                    trip[(u32)ej] = TRIP(f, cum, T);
+                    B[s] = f + 2; T += 2;
+                }
+            }
+            T = __shfl_sync(0xFFFFFFFFu, T, 0);
+            __syncwarp();
+        } else {
+            if (N <= 32) {
+                const u32 v = ln < N ? B[ln] : 0u;
+                const u32 inc = warp_incl_sum(v);
+                if (ln < N) P[ln] = inc - v;
+            } else {
+                const u32 per = N / 32, b0 = ln * per; u32 s = 0;
+                for (u32 k = 0; k < per; ++k) { const u32 t = B[b0 + k]; P[b0 + k] = s; s += t; }
+                const u32 off = warp_incl_sum(s) - s;
+                for (u32 k = 0; k < per; ++k) P[b0 + k] += off;
+            }
+            __syncwarp();
+            u32 peers = 0;
+            if (valid) peers = __match_any_sync(vm, sym);
+            u32 c_lt = 0, rem = vm;
+            while (rem) {                              // warp-uniform: one step per distinct symbol of the row
+                const int leader = __ffs(rem) - 1;
+                const u32 gs = __shfl_sync(0xFFFFFFFFu, sym, leader);
+                const u32 gm = __shfl_sync(0xFFFFFFFFu, peers, leader);
+                if (valid && gs < sym) c_lt += __popc(gm & lt);
+                rem &= ~gm;
+            }
+            if (valid) trip[(u32)e] = TRIP(B[sym] + 2 * __popc(peers & lt), P[sym] + 2 * c_lt, T + 2 * __popc(vm & lt));
+            __syncwarp();
+            if (valid && (__ffs(peers) - 1) == (int)ln) B[sym] += 2 * __popc(peers);
+            T += 2 * nv;
+            __syncwarp();
+        }
+        if (nv < 32) break;
+    }
+}
+
 // walk the context runs of the sorted array and emit the adaptive-model triple of every symbol
-// (TSymbolCoderRC<N>::EncodeSymbol / Accumulate / Rescale, src/SymbolCoderRC.h:35-48, 69-90)
-__device__ void group_scan(ModelShared& S, const u64* sorted, u64* trip, u32 M)
+// (TSymbolCoderRC<N>::EncodeSymbol / Accumulate / Rescale, src/SymbolCoderRC.h:35-48, 69-90):
+// short runs one thread each (N 16-bit counters per thread in shared memory), long runs one warp each.
+__device__ void group_scan(ModelShared& S, const u64* sorted, u64* trip, u32 M, const Workspace& ws, long long& prof_t, int prof_base)
 {
     const u32 N = S.cfg.alpha;
     const u32 nthr = min((u32)DSRC_CTA, (u32)(CNT_BYTES / 2) / N);
     const u32 limit = (1u << 16) - 2 * N;
     const u32 tid = threadIdx.x;
-    if (tid >= nthr) return;
-    u16* cnt = S.u.cnt + tid;                        // counter of symbol s at cnt[s * nthr]
-    for (u32 i = tid; i < M; i += nthr) {
-        const u64 e0 = sorted[i];
-        const u64 key = e0 >> 40;
-        if (i > 0 && (sorted[i - 1] >> 40) == key) continue;     // not a run head
-        u64 e = e0;
-        u32 k = i;
-        const bool single = (k + 1 >= M) || ((sorted[k + 1] >> 40) != key);
-        if (single) {                                 // fresh row: all ones
-            const u32 s = (u32)(e >> 32) & 255u;
-            trip[(u32)e] = 1ull | ((u64)s << 16) | ((u64)N << 32);
-            continue;
-        }
-        for (u32 s = 0; s < N; ++s) cnt[s * nthr] = 1;
-        u32 tot = N;
-        for (;;) {
-            const u32 s = (u32)(e >> 32) & 255u;
-            if (tot >= limit) {                       // Rescale: stats[i] -= stats[i] >> 1
-                tot = 0;
-                for (u32 q = 0; q < N; ++q) { u32 c = cnt[q * nthr]; c -= c >> 1; cnt[q * nthr] = (u16)c; tot += c; }
+    if (tid == 0) S.n_long = 0;
+    __syncthreads();
+    if (tid < nthr) {
+        u16* cnt = S.u.cnt + tid;                        // counter of symbol s at cnt[s * nthr]
+        for (u32 i = tid; i < M; i += nthr) {
+            const u64 e0 = sorted[i];
+            const u64 key = e0 >> 40;
+            if (i > 0 && (sorted[i - 1] >> 40) == key) continue;     // not a run head
+            u64 nx = (i + 1 < M) ? sorted[i + 1] : ~0ull;             // ~0 is never a key (contexts have <= 21 bits)
+            if ((nx >> 40) != key) {                      // fresh row: all ones
+                const u32 s = (u32)(e0 >> 32) & 255u;
+                trip[(u32)e0] = TRIP(1, s, N);
+                continue;
             }
-            const u32 f = cnt[s * nthr];
-            u32 cum = 0;
-            if (s * 2 <= N) { for (u32 q = 0; q < s; ++q) cum += cnt[q * nthr]; }
-            else { u32 hi = 0; for (u32 q = s; q < N; ++q) hi += cnt[q * nthr]; cum = tot - hi; }
-            trip[(u32)e] = (u64)f | ((u64)cum << 16) | ((u64)tot << 32);
-            cnt[s * nthr] = (u16)(f + 2); tot += 2;
-            if (++k >= M) break;
-            e = sorted[k];
-            if ((e >> 40) != key) break;
+            if (i + LONG_T < M && (sorted[i + LONG_T] >> 40) == key) {
+                const u32 slot = atomicAdd(&S.n_long, 1u);
+                if (slot < LONGQ_MAX) { S.longq[slot] = i; continue; }
+            }
+            for (u32 s = 0; s < N; ++s) cnt[s * nthr] = 1;
+            u32 tot = N, k = i;
+            u64 e = e0;
+            for (;;) {
+                const u32 s = (u32)(e >> 32) & 255u;
+                if (tot >= limit) {                       // Rescale: stats[i] -= stats[i] >> 1
+                    tot = 0;
+                    for (u32 q = 0; q < N; ++q) { u32 c = cnt[q * nthr]; c -= c >> 1; cnt[q * nthr] = (u16)c; tot += c; }
+                }
+                const u32 f = cnt[s * nthr];
+                u32 cum = 0;
+                if (s * 2 <= N) { for (u32 q = 0; q < s; ++q) cum += cnt[q * nthr]; }
+                else { u32 hi = 0; for (u32 q = s; q < N; ++q) hi += cnt[q * nthr]; cum = tot - hi; }
+                trip[(u32)e] = TRIP(f, cum, tot);
+                cnt[s * nthr] = (u16)(f + 2); tot += 2;
+                e = nx; ++k;
+                if ((e >> 40) != key) break;
+                nx = (k + 1 < M) ? sorted[k + 1] : ~0ull;
+            }
         }
     }
+    __syncthreads();
+    PROF_MARK(prof_base + 2);
+    const u32 n_long = min(S.n_long, (u32)LONGQ_MAX);
+    for (u32 r = warp_id(); r < n_long; r += DSRC_WARPS) warp_run(S, sorted, trip, M, S.longq[r]);
+    __syncthreads();
+    PROF_MARK(prof_base + 3);
 }
 
 template <bool QUALITY>
@@ -192,6 +281,8 @@ __global__ void __launch_bounds__(DSRC_CTA) k_model(Workspace ws, u64 arena_stri
     const u32 tid = threadIdx.x;
     u64* bufA = ws.elem_a + (u64)blockIdx.x * arena_stride;
     u64* bufB = ws.elem_b + (u64)blockIdx.x * arena_stride;
+    long long prof_t = ws.prof ? clock64() : 0;
+    const int prof_base = QUALITY ? 0 : 8;
 
     for (u32 blk = blockIdx.x; blk < ws.n_blocks; blk += gridDim.x) {
         const BlockDesc& d = ws.desc[blk];
@@ -271,14 +362,16 @@ __global__ void __launch_bounds__(DSRC_CTA) k_model(Workspace ws, u64 arena_stri
             }
         }
         __syncthreads();
+        PROF_MARK(prof_base + 0);
         // ---- stable LSD radix sort by context
         u64* src = bufA; u64* dst = bufB;
         for (u32 p = 0; p < passes; ++p) {
             sort_pass(S, src, dst, M, 40 + 8 * p, S.u.s.hist[p & 1], (p + 1 < passes) ? S.u.s.hist[(p + 1) & 1] : nullptr);
             u64* t = src; src = dst; dst = t;
         }
+        PROF_MARK(prof_base + 1);
         // ---- adaptive statistics per context run
-        group_scan(S, src, (QUALITY ? ws.trip_q : ws.trip_d) + d.sym_base, M);
+        group_scan(S, src, (QUALITY ? ws.trip_q : ws.trip_d) + d.sym_base, M, ws, prof_t, prof_base);
     }
 }
 

@@ -107,8 +107,11 @@ float dsrcgpu_last_call_ms(dsrcgpu_ctx* ctx);
 /* Measurement support: device time (ms, CUDA events on the context's streams) spent in each kernel family during
  * the last encode/decode call, and launch counts. names[i] are static strings. Returns the number of entries. */
 int dsrcgpu_last_kernel_times(dsrcgpu_ctx* ctx, const char** names, float* ms, uint32_t* launches, int max_entries);
-/* enable (1) / disable (0) per-kernel event timing (adds stream synchronisation; off by default) */
+/* bit 0: per-kernel event timing; bit 1: in-kernel phase cycle counters (clock64 of thread 0 of every CTA, summed
+ * over CTAs; slot map in DESIGN.md "instrumentation"). */
 void dsrcgpu_set_profiling(dsrcgpu_ctx* ctx, int on);
+/* copies the 64 phase counters accumulated since the last reset */
+int dsrcgpu_phase_cycles(dsrcgpu_ctx* ctx, uint64_t* out64, int reset);
 
 /* Device allocation helpers so a host language without a CUDA binding can stage resident inputs. */
 int dsrcgpu_device_alloc(dsrcgpu_ctx* ctx, uint64_t bytes, void** d_ptr);

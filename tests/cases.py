@@ -29,4 +29,7 @@ def small_cases():
     c.append(("ill_startbig_d6_q2", synth.illumina(700, seed=18, start_index=99990), 6, 2, 0))
     c.append(("q1_valuevar_d6_q2", synth.illumina(40, seed=2, small_field=True), 6, 2, 0))
     c.append(("q1_valuevar_big_d0_q0", synth.illumina(900, seed=3, small_field=True), 0, 0, 0))
+    sk = synth.skewed(5000)
+    for d, q in [(6, 2), (9, 1), (3, 2)]:
+        c.append(("skewed_rescale_d%d_q%d" % (d, q), sk, d, q, 0))
     return c
