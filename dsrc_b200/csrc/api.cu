@@ -44,7 +44,8 @@ struct dsrcgpu_ctx {
     DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
     DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
     // persistent per-CTA arenas
-    DevBuf elem_a, elem_b, tagpool, dec_arena, q0_arena, prof;
+    DevBuf elem_a, elem_b, tagpool, dec_arena, q0_arena, prof, tab;
+    u64 tab_stride = 0;
     bool phase_prof = false;
     u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0; u32 q0_ctas = 0; u64 q0_stride = 0;
     // pinned host staging
@@ -111,6 +112,12 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     u64 ctas = std::min<u64>((u64)ctx->sms * 4, std::max<u64>(1, (16ull << 30) / per_cta));
     ctas = std::min<u64>(ctas, max_inflight_blocks);
     ctx->model_ctas = (u32)ctas;
+    {   // adaptive-row tables of the tile/table model engine: rows of 2N bytes, one table per persistent CTA
+        u64 tq = 0, td = 0;
+        if (settings->quality_order == 1) tq = (1ull << 16) * 32; else if (settings->quality_order == 2) tq = (1ull << 20) * 32;   // <16,3,*> / <16,4,*>
+        if (settings->dna_order) { const u32 o = settings->dna_order, o8 = o > 7 ? 7 : o; td = std::max<u64>((1ull << (2 * o)) * 8, (1ull << (3 * o8)) * 16); }
+        ctx->tab_stride = std::max(tq, td);
+    }
     ctx->tag_ctas = (u32)std::min<u64>((u64)ctx->sms * 4, max_inflight_blocks);
     ctx->q0_stride = q0_arena_bytes(max_block_bytes);
     ctx->q0_ctas = (u32)std::min<u64>(std::min<u64>((u64)ctx->sms * 2, max_inflight_blocks), std::max<u64>(1, (16ull << 30) / ctx->q0_stride));
@@ -125,7 +132,7 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->in, &ctx->desc, &ctx->state, &ctx->result, &ctx->probe, &ctx->lines, &ctx->qcat, &ctx->dcat, &ctx->trip_q, &ctx->trip_d,
                       &ctx->ftab, &ctx->streams, &ctx->out, &ctx->r_title_off, &ctx->r_seq_off, &ctx->r_qua_off, &ctx->r_title_len, &ctx->r_qua_len,
-                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena, &ctx->q0_arena, &ctx->prof};
+                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena, &ctx->q0_arena, &ctx->prof, &ctx->tab};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -248,6 +255,10 @@ static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, con
     CK(ctx->ftab.ensure(ftab * 8));
     CK(ctx->streams.ensure(streams));
     if (rc_q || rc_d) { CK(ctx->elem_a.ensure(ctx->model_stride * 8 * ctx->model_ctas)); CK(ctx->elem_b.ensure(ctx->model_stride * 8 * ctx->model_ctas)); }
+    if ((rc_q || rc_d) && !ctx->tab.p && ctx->tab_stride) {
+        CK(ctx->tab.ensure(ctx->tab_stride * ctx->model_ctas));
+        CK(cudaMemsetAsync(ctx->tab.p, 0, ctx->tab.cap, s));      // invariant between blocks: first counter of every row is 0
+    }
     CK(ctx->tagpool.ensure(tagpool_bytes_per_block() * ctx->tag_ctas));
     if (!rc_q || !rc_d) CK(ctx->q0_arena.ensure(ctx->q0_stride * ctx->q0_ctas));
 
@@ -259,6 +270,7 @@ static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, con
     ws.trip_q = (u64*)ctx->trip_q.p; ws.trip_d = (u64*)ctx->trip_d.p;
     ws.elem_a = (u64*)ctx->elem_a.p; ws.elem_b = (u64*)ctx->elem_b.p;
     ws.ftab = (u64*)ctx->ftab.p; ws.streams = (u8*)ctx->streams.p;
+    ws.tab = (u8*)ctx->tab.p; ws.tab_stride = ctx->tab_stride;
     ws.tagpool = (u8*)ctx->tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
 
     CK(cudaMemcpyAsync(ctx->desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));

@@ -102,6 +102,7 @@ struct Workspace {
     u32 qoff;                   // quality offset
     u32 plus_rep;
     u32 dna_order, qua_order;
+    u8* tab; u64 tab_stride;    // per-CTA adaptive-row tables of the tile/table model engine (zero between blocks)
     u64* prof;                  // optional: 64 phase cycle counters (clock64 deltas of thread 0 of every CTA), or null
 };
 

@@ -1,0 +1,269 @@
+// Tile/table engine of the order-k modelers for alphabets of <= 16 symbols (DNA 4/8-symbol rows, 16-symbol quality rows).
+//
+// The block's symbols are taken in their original order, 2048 at a time. Inside a tile the symbols are grouped by context
+// with a stable radix sort that never leaves shared memory; every context group then meets its adaptive row exactly as
+// TSymbolCoderRC<N>::EncodeSymbol would (src/SymbolCoderRC.h:35-48,69-90): one thread (short groups) or one warp (long
+// groups) loads the row from the per-CTA table in HBM/L2 -- the same table the reference keeps per coder
+// (DnaModelerRCO.h:94-119, QualityEncoder.h:45-58), rows of 2N bytes -- walks the group's symbols in order, emits their
+// (freq, cum, tot) triples into a shared-memory staging tile and writes the row back. The staged triples leave in one
+// coalesced store. A row whose first counter is 0 has not been touched by this block (counters never drop below 1), so
+// the table needs no per-block initialisation: touched contexts are remembered and re-zeroed when the block is done.
+#pragma once
+
+#define TT 2048                               // symbols per tile
+#define TT_SHIFT 11
+
+struct TabShared {
+    u32 el[2][TT];                            // (ctx << 11) | position in tile, ping-pong of the in-tile sort
+    u8 sym[TT];
+    union { u64 trip[TT]; u16 H[DSRC_WARPS << 10]; } x;   // triple staging / sort counters (never live together)
+    u16 heads[TT];
+    u16 longs[TT / LONG_T + 2];
+    u32 B[DSRC_WARPS][16], P[DSRC_WARPS][16];
+    u32 n_heads, n_long, n_touched;
+};
+
+__device__ __forceinline__ void tile_sort_pass(TabShared& S, u32* scan, const u32* src, u32* dst, u32 n, u32 shift, u32 bits)
+{
+    const u32 tid = threadIdx.x, w = warp_id(), ln = lane_id(), lt = (1u << ln) - 1;
+    const u32 bins = 1u << bits, dmask = bins - 1;
+    const u32 wb = min(n, w * (TT / DSRC_WARPS)), we = min(n, wb + TT / DSRC_WARPS);
+    u16* H = S.x.H + w * bins;
+    for (u32 i = tid; i < DSRC_WARPS * bins; i += DSRC_CTA) S.x.H[i] = 0;
+    __syncthreads();
+    for (u32 r = wb; r < we; r += 32) {
+        const u32 i = r + ln; const bool in = i < we;
+        const u32 d = in ? (src[i] >> shift) & dmask : 0u;
+        const u32 am = __ballot_sync(FULL, in);
+        if (in) { const u32 peers = __match_any_sync(am, d); if ((__ffs(peers) - 1) == (int)ln) H[d] += (u16)__popc(peers); }
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const u32 per = bins > DSRC_CTA ? bins / DSRC_CTA : 1u, d0 = tid * per;
+        u32 sum = 0;
+        if (d0 < bins) for (u32 k = 0; k < per; ++k) for (u32 ww = 0; ww < DSRC_WARPS; ++ww) sum += S.x.H[ww * bins + d0 + k];
+        u32 total, run = block_excl_sum(sum, scan, &total);
+        if (d0 < bins) for (u32 k = 0; k < per; ++k) for (u32 ww = 0; ww < DSRC_WARPS; ++ww) { const u32 c = S.x.H[ww * bins + d0 + k]; S.x.H[ww * bins + d0 + k] = (u16)run; run += c; }
+    }
+    __syncthreads();
+    for (u32 r = wb; r < we; r += 32) {
+        const u32 i = r + ln; const bool in = i < we;
+        const u32 e = in ? src[i] : 0u;
+        const u32 d = (e >> shift) & dmask;
+        const u32 am = __ballot_sync(FULL, in);
+        if (in) {
+            const u32 peers = __match_any_sync(am, d);
+            const u32 pos = H[d] + __popc(peers & lt);
+            __syncwarp(am);
+            if ((__ffs(peers) - 1) == (int)ln) H[d] += (u16)__popc(peers);
+            dst[pos] = e;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// counter k of a row held as N/2 packed u16 pairs
+template <int N> struct RowRegs {
+    u32 c[N / 2];
+    __device__ __forceinline__ void load(const u8* p)
+    {
+        if (N == 4) { const uint2 v = *(const uint2*)p; c[0] = v.x; c[1] = v.y; }
+        else {
+#pragma unroll
+            for (int k = 0; k < N / 8; ++k) { const uint4 v = ((const uint4*)p)[k]; c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w; }
+        }
+    }
+    __device__ __forceinline__ void store(u8* p) const
+    {
+        if (N == 4) *(uint2*)p = make_uint2(c[0], c[1]);
+        else {
+#pragma unroll
+            for (int k = 0; k < N / 8; ++k) ((uint4*)p)[k] = make_uint4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
+        }
+    }
+    __device__ __forceinline__ void ones() {
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) c[k] = 0x00010001u;
+    }
+    __device__ __forceinline__ u32 total() const { u32 t = 0;
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) t += (c[k] & 0xFFFFu) + (c[k] >> 16);
+        return t; }
+    __device__ __forceinline__ u32 rescale() { u32 t = 0;      // stats[i] -= stats[i] >> 1
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) { u32 lo = c[k] & 0xFFFFu, hi = c[k] >> 16; lo -= lo >> 1; hi -= hi >> 1; c[k] = lo | (hi << 16); t += lo + hi; }
+        return t; }
+    __device__ __forceinline__ void get(u32 s, u32& f, u32& cum) const { f = 0; cum = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const u32 v = (c[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu; cum += (u32)k < s ? v : 0u; f = (u32)k == s ? v : f; } }
+    __device__ __forceinline__ void bump(u32 s) {
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) c[k] += (u32)k == (s >> 1) ? (2u << ((s & 1) * 16)) : 0u; }
+};
+
+template <int N>
+__device__ void tab_short_groups(TabShared& S, const u32* sorted, u32 n, u8* tab, u32* touched)
+{
+    const u32 limit = (1u << 16) - 2 * N;
+    const u32 nh = S.n_heads;
+    for (u32 h = threadIdx.x; h < nh; h += DSRC_CTA) {
+        u32 p = S.heads[h];
+        u32 e = sorted[p];
+        const u32 key = e >> TT_SHIFT;
+        u8* rowp = tab + (u64)key * (2 * N);
+        RowRegs<N> R; R.load(rowp);
+        if ((R.c[0] & 0xFFFFu) == 0) { R.ones(); touched[atomicAdd(&S.n_touched, 1u)] = key; }
+        u32 tot = R.total();
+        do {
+            const u32 pos = e & (TT - 1), s = S.sym[pos];
+            if (tot >= limit) tot = R.rescale();
+            u32 f, cum; R.get(s, f, cum);
+            S.x.trip[pos] = TRIP(f, cum, tot);
+            R.bump(s); tot += 2;
+            if (++p >= n) break;
+            e = sorted[p];
+        } while ((e >> TT_SHIFT) == key);
+        R.store(rowp);
+    }
+}
+
+// one warp per long group; 32 members per step (see warp_run in rc_model.cu for the row algebra)
+template <int N>
+__device__ void tab_long_groups(TabShared& S, const u32* sorted, u32 n, u8* tab, u32* touched)
+{
+    const u32 limit = (1u << 16) - 2 * N, ln = lane_id(), lt = (1u << ln) - 1;
+    u32* B = S.B[warp_id()]; u32* P = S.P[warp_id()];
+    const u32 nl = S.n_long;
+    for (u32 g = warp_id(); g < nl; g += DSRC_WARPS) {
+        const u32 a = S.longs[g];
+        const u32 key = sorted[a] >> TT_SHIFT;
+        u16* rowp = (u16*)(tab + (u64)key * (2 * N));
+        u32 v = ln < N ? rowp[ln] : 0u;
+        const bool fresh = __shfl_sync(FULL, v, 0) == 0;
+        if (fresh) { v = ln < N ? 1u : 0u; if (ln == 0) touched[atomicAdd(&S.n_touched, 1u)] = key; }
+        if (ln < N) B[ln] = v;
+        u32 T = warp_red_sum(v);
+        __syncwarp();
+        for (u32 row = a;; row += 32) {
+            const u32 i = row + ln;
+            const u32 e = i < n ? sorted[i] : 0xFFFFFFFFu;
+            const bool valid = i < n && (e >> TT_SHIFT) == key;
+            const u32 vm = __ballot_sync(FULL, valid);
+            if (!vm) break;
+            const u32 nv = __popc(vm);
+            const u32 pos = e & (TT - 1);
+            const u32 sym = valid ? S.sym[pos] : 0u;
+            if (T + 2 * (nv - 1) >= limit) {
+                for (u32 j = 0; j < nv; ++j) {                 // replay the row symbol by symbol (lane 0 computes)
+                    const u32 sj = __shfl_sync(FULL, sym, j), pj = __shfl_sync(FULL, pos, j);
+                    if (ln == 0) {
+                        if (T >= limit) { T = 0; for (u32 q = 0; q < N; ++q) { u32 c = B[q]; c -= c >> 1; B[q] = c; T += c; } }
+                        const u32 f = B[sj]; u32 cum = 0;
+                        for (u32 q = 0; q < sj; ++q) cum += B[q];
+                        S.x.trip[pj] = TRIP(f, cum, T);
+                        B[sj] = f + 2; T += 2;
+                    }
+                }
+                T = __shfl_sync(FULL, T, 0);
+                __syncwarp();
+            } else {
+                const u32 bv = ln < N ? B[ln] : 0u;
+                const u32 inc = warp_incl_sum(bv);
+                if (ln < N) P[ln] = inc - bv;
+                __syncwarp();
+                u32 peers = 0;
+                if (valid) peers = __match_any_sync(vm, sym);
+                u32 c_lt = 0, rem = vm;
+                while (rem) {
+                    const int leader = __ffs(rem) - 1;
+                    const u32 gs = __shfl_sync(FULL, sym, leader);
+                    const u32 gm = __shfl_sync(FULL, peers, leader);
+                    if (valid && gs < sym) c_lt += __popc(gm & lt);
+                    rem &= ~gm;
+                }
+                if (valid) S.x.trip[pos] = TRIP(B[sym] + 2 * __popc(peers & lt), P[sym] + 2 * c_lt, T + 2 * __popc(vm & lt));
+                __syncwarp();
+                if (valid && (__ffs(peers) - 1) == (int)ln) B[sym] += 2 * __popc(peers);
+                T += 2 * nv;
+                __syncwarp();
+            }
+            if (nv < 32) break;
+        }
+        if (ln < N) rowp[ln] = (u16)B[ln];
+        __syncwarp();
+    }
+}
+
+// F: FetchQ / FetchD (rc_model.cu). scratch: per-CTA global scratch for the touched-context list (M entries).
+template <int N, class F>
+__device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8* tab, u32* touched, u64* trip,
+                           const Workspace& ws, long long& prof_t, int pb)
+{
+    const u32 tid = threadIdx.x, w = warp_id(), ln = lane_id(), lt = (1u << ln) - 1;
+    const u32 passes = (key_bits + 9) / 10, pbits = (key_bits + passes - 1) / passes;
+    if (tid == 0) S.n_touched = 0;
+    for (u32 t0 = 0; t0 < M; t0 += TT) {
+        const u32 n = min((u32)TT, M - t0);
+        __syncthreads();
+        if (tid == 0) { S.n_heads = 0; S.n_long = 0; }
+        // contexts of the tile, in original order
+        {
+            const u32 wb = w * (TT / DSRC_WARPS);
+            f.begin(t0 + wb);
+            typename F::Raw raw[TT / DSRC_WARPS / 32];
+#pragma unroll
+            for (int r = 0; r < TT / DSRC_WARPS / 32; ++r) { const u32 p = wb + r * 32 + ln; raw[r] = f.ld(t0 + p, p < n); }
+#pragma unroll
+            for (int r = 0; r < TT / DSRC_WARPS / 32; ++r) {
+                const u32 p = wb + r * 32 + ln; const bool in = p < n;
+                const u64 e = f.mk(raw[r], t0 + p, in);
+                if (in) { S.el[0][p] = ((u32)(e >> 40) << TT_SHIFT) | p; S.sym[p] = (u8)(e >> 32); }
+            }
+        }
+        __syncthreads();
+        PROF_MARK(pb + 0);
+        u32 cur = 0;
+        for (u32 ps = 0; ps < passes; ++ps) { tile_sort_pass(S, scan, S.el[cur], S.el[cur ^ 1], n, TT_SHIFT + ps * pbits, pbits); cur ^= 1; }
+        const u32* sorted = S.el[cur];
+        PROF_MARK(pb + 1);
+        // group heads
+        for (u32 p0 = 0; p0 < n; p0 += DSRC_CTA) {
+            const u32 p = p0 + tid; const bool in = p < n;
+            const u32 key = in ? sorted[p] >> TT_SHIFT : 0u;
+            bool push = false;
+            if (in && (p == 0 || (sorted[p - 1] >> TT_SHIFT) != key)) {
+                if (p + LONG_T < n && (sorted[p + LONG_T] >> TT_SHIFT) == key) S.longs[atomicAdd(&S.n_long, 1u)] = (u16)p;
+                else push = true;
+            }
+            const u32 m = __ballot_sync(FULL, push);
+            if (m) {
+                u32 base = 0;
+                const int leader = __ffs(m) - 1;
+                if ((int)ln == leader) base = atomicAdd(&S.n_heads, (u32)__popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                if (push) S.heads[base + __popc(m & lt)] = (u16)p;
+            }
+        }
+        __syncthreads();
+        PROF_MARK(pb + 2);
+        tab_short_groups<N>(S, sorted, n, tab, touched);
+        if (ws.prof) { __syncthreads(); PROF_MARK(pb + 3); }
+        tab_long_groups<N>(S, sorted, n, tab, touched);
+        __syncthreads();
+        PROF_MARK(pb + 4);
+        for (u32 p = tid; p < n; p += DSRC_CTA) trip[t0 + p] = S.x.trip[p];
+        PROF_MARK(pb + 5);
+    }
+    __syncthreads();
+    // leave the table as it was found: first counter 0 == untouched
+    const u32 nt = S.n_touched;
+    for (u32 k = tid; k < nt; k += DSRC_CTA) {       // whole rows: the next block (or the other stream) may use another row size
+        u8* rowp = tab + (u64)touched[k] * (2 * N);
+        if (N == 4) *(uint2*)rowp = make_uint2(0u, 0u);
+        else for (int j = 0; j < N / 8; ++j) ((uint4*)rowp)[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    PROF_MARK(pb + 6);
+}

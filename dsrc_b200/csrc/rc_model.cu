@@ -19,9 +19,11 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#define SORT_E 8                              // elements per thread per tile
-#define SORT_TILE (DSRC_CTA * SORT_E)
-#define CNT_BYTES 32768                       // shared budget for the per-thread symbol counters
+#define SORT_MAX_BITS 10                      // radix digits of at most 10 bits: 8 warps x 1024 counters = 32 KB
+#define LONG_T 48                             // context runs longer than this are walked by a whole warp
+#define SCAN_TILE 2048                        // sorted elements staged in shared memory per step of the run walker
+#define SCAN_LOOK (LONG_T + 1)
+#define FULL 0xFFFFFFFFu
 
 struct ModelCfg {
     u32 alpha, bits, key_bits, sym_order, rescale, ord;   // ord: DNA order; sym_order/rescale: quality
@@ -58,99 +60,147 @@ __device__ void dna_cfg(u32 order, u32 scheme, ModelCfg& c)
     c.key_bits = c.ord * c.bits; c.sym_order = 0; c.rescale = 0;
 }
 
-#define LONG_T 48                              // context runs longer than this are walked by a whole warp
-#define LONGQ_MAX 2048
+#define TRIP(f, cum, tot) ((u64)(f) | ((u64)(cum) << 16) | ((u64)(tot) << 32))
+#define PROF_MARK(slot) do { if (ws.prof && threadIdx.x == 0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&ws.prof[slot], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
+#include "model_tab.cuh"
 
 struct ModelShared {
     union {
-        struct {
-            u32 off[DSRC_WARPS][256];
-            u16 wcnt[DSRC_WARPS][256];
-            u32 base[256];
-            u32 hist[2][256];
-        } s;
-        u16 cnt[CNT_BYTES / 2];
-        struct { u32 B[DSRC_WARPS][128]; u32 P[DSRC_WARPS][128]; } l;   // per-warp row state of the long-run walker
+        u32 H[DSRC_WARPS << SORT_MAX_BITS];        // sort: per-warp digit counters, then scatter offsets
+        union {
+            struct { u64 tile[SCAN_TILE + SCAN_LOOK]; u16 heads[SCAN_TILE]; u8 cnt[16384]; } t;   // short-run walker
+            struct { u32 B[DSRC_WARPS][128]; u32 P[DSRC_WARPS][128]; } l;                        // long-run walker: per-warp row state
+        } g;
+        TabShared tab;                             // tile/table engine (model_tab.cuh)
     } u;
-    u32 longq[LONGQ_MAX];
-    u32 n_long;
+    u32 scan[DSRC_WARPS + 1];
+    u32 n_long, n_heads;
     u8 rank[256];
     ModelCfg cfg;
     u32 M, ok;
 };
 
-#define PROF_MARK(slot) do { if (ws.prof && threadIdx.x == 0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&ws.prof[slot], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
 
-__device__ __forceinline__ void hist_add(u32* hist, u32 digit, bool active)
-{
-    u32 am = __ballot_sync(0xFFFFFFFFu, active);
-    if (active) {
-        u32 peers = __match_any_sync(am, digit);
-        if ((__ffs(peers) - 1) == (int)lane_id()) atomicAdd(&hist[digit], __popc(peers));
-    }
-}
-
-// one stable LSD pass (8-bit digit at `shift`) from src to dst; hist_cur = counts of this digit,
-// hist_next (may be null) accumulates the counts of the next digit while scattering.
-__device__ void sort_pass(ModelShared& S, const u64* src, u64* dst, u32 M, u32 shift,
-                          u32* hist_cur, u32* hist_next)
-{
-    const u32 tid = threadIdx.x, w = warp_id(), ln = lane_id();
-    // exclusive scan of the 256 digit counts
+// ---- element sources of a sort pass. An element is (ctx << 40) | (sym << 32) | index. A warp walks consecutive rows of
+// 32 symbols; the symbols a context needs from before the row come from the neighbouring lanes / the previous row.
+struct FetchSorted {
+    typedef u64 Raw;
+    const u64* src;
+    __device__ __forceinline__ void begin(u32) {}
+    __device__ __forceinline__ Raw ld(u32 i, bool in) const { return in ? src[i] : 0ull; }
+    __device__ __forceinline__ u64 mk(Raw r, u32, bool) { return r; }
+};
+// quality context (TQualityModelBase::UpdateHash/GetHash, QualityEncoder.h:77-94; position bucket :307)
+struct FetchQ {
+    typedef u32 Raw;
+    const u8* q; const u8* pctx; const u8* rank; u32 so, h, bits, M; u32 prev;
+    __device__ __forceinline__ void begin(u32 start) { const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? rank[q[j]] : 0u; }
+    __device__ __forceinline__ Raw ld(u32 i, bool in) const { return in ? ((u32)q[i] | ((u32)pctx[i] << 8)) : 0u; }
+    __device__ __forceinline__ u64 mk(Raw raw, u32 i, bool in)
     {
-        u32 v = hist_cur[tid];
-        u32 inc = warp_incl_sum(v);
-        __shared__ u32 wsum[DSRC_WARPS];
-        if (ln == 31) wsum[w] = inc;
-        __syncthreads();
-        u32 b = 0;
-        for (u32 k = 0; k < w; ++k) b += wsum[k];
-        S.u.s.base[tid] = b + inc - v;
-        for (u32 k = 0; k < DSRC_WARPS; ++k) S.u.s.wcnt[k][tid] = 0;
-        if (hist_next) hist_next[tid] = 0;
-        __syncthreads();
-    }
-    for (u32 tile = 0; tile < M; tile += SORT_TILE) {
-        u64 e[SORT_E]; u32 rk[SORT_E];
-        const u32 wbase = tile + w * (32 * SORT_E);
+        const u32 ln = lane_id();
+        const u32 r0 = in ? rank[raw & 255u] : 0u;
+        u32 y[6]; y[0] = r0;                          // y[k] = symbol k steps back (0 before the block start)
 #pragma unroll
-        for (int k = 0; k < SORT_E; ++k) {
-            const u32 i = wbase + k * 32 + ln;
-            const bool in = i < M;
-            e[k] = in ? src[i] : 0;
-            const u32 dg = (u32)(e[k] >> shift) & 255u;
-            const u32 am = __ballot_sync(0xFFFFFFFFu, in);
-            rk[k] = 0;
+        for (int k = 1; k < 6; ++k) {
+            const u32 a = __shfl_up_sync(FULL, r0, k), b = __shfl_sync(FULL, prev, (ln + 32 - k) & 31);
+            y[k] = ln >= (u32)k ? a : b;
+        }
+        prev = r0;
+        u32 hash = 0;                                 // raw symbols below slot h, pairwise means from slot h on
+        if (so == 1) hash = y[1];
+        else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if ((u32)t < so) { const u32 v = (u32)t < h ? y[t + 1] : ((y[t + 1] + y[t + 2]) >> 1); hash |= v << (t * bits); }
+        }
+        if (!in) return 0ull;
+        const u32 ctx = (hash << bits) | (raw >> 8);
+        return ((u64)ctx << 40) | ((u64)r0 << 32) | i;
+    }
+};
+// DNA context: the previous `ord` symbols (TDnaRCOrderModeler, DnaModelerRCO.h:45-62)
+struct FetchD {
+    typedef u32 Raw;
+    const u8* sq; u32 ord, bits, M; u32 prev;
+    __device__ __forceinline__ void begin(u32 start) { const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? sq[j] : 0u; }
+    __device__ __forceinline__ Raw ld(u32 i, bool in) const { return in ? sq[i] : 0u; }
+    __device__ __forceinline__ u64 mk(Raw r0, u32 i, bool in)
+    {
+        const u32 ln = lane_id(), mask = (1u << bits) - 1;
+        u32 ctx = 0;
+        for (u32 t = 0; t < ord; ++t) {
+            const u32 k = t + 1;
+            const u32 a = __shfl_up_sync(FULL, r0, k), b = __shfl_sync(FULL, prev, (ln + 32 - k) & 31);
+            ctx |= ((ln >= k ? a : b) & mask) << (t * bits);
+        }
+        prev = r0;
+        return in ? (((u64)ctx << 40) | ((u64)r0 << 32) | i) : 0ull;
+    }
+};
+
+// One stable counting-sort pass on the `bits`-wide digit at `shift`. Every warp owns a contiguous eighth of the input:
+// it histograms its part into its own counters, the counters are scanned in (digit, warp) order, and each warp
+// scatters its part in order through its own running offsets -- no CTA barrier inside the two loops.
+#define SORT_U 4                                // rows in flight per warp (memory-level parallelism)
+template <class F>
+__device__ void sort_pass(ModelShared& S, F f, u64* dst, u32 M, u32 shift, u32 bits)
+{
+    const u32 tid = threadIdx.x, w = warp_id(), ln = lane_id(), lt = (1u << ln) - 1;
+    const u32 bins = 1u << bits, dmask = bins - 1;
+    const u32 seg = (((M + DSRC_WARPS - 1) / DSRC_WARPS) + 31) & ~31u;
+    const u32 wb = min(M, w * seg), we = min(M, wb + seg);
+    u32* H = S.u.H + w * bins;
+    for (u32 i = tid; i < DSRC_WARPS * bins; i += DSRC_CTA) S.u.H[i] = 0;
+    __syncthreads();
+    f.begin(wb);
+    for (u32 r = wb; r < we; r += 32 * SORT_U) {
+        typename F::Raw raw[SORT_U];
+#pragma unroll
+        for (int k = 0; k < SORT_U; ++k) { const u32 i = r + k * 32 + ln; raw[k] = f.ld(i, i < we); }
+#pragma unroll
+        for (int k = 0; k < SORT_U; ++k) {
+            const u32 i = r + k * 32 + ln; const bool in = i < we;
+            if (r + k * 32 >= we) break;
+            const u64 e = f.mk(raw[k], i, in);
+            const u32 d = (u32)(e >> shift) & dmask;
+            const u32 am = __ballot_sync(FULL, in);
+            if (in) { const u32 peers = __match_any_sync(am, d); if ((__ffs(peers) - 1) == (int)ln) H[d] += __popc(peers); }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    {
+        const u32 per = bins > DSRC_CTA ? bins / DSRC_CTA : 1u, d0 = tid * per;
+        u32 sum = 0;
+        if (d0 < bins) for (u32 k = 0; k < per; ++k) for (u32 ww = 0; ww < DSRC_WARPS; ++ww) sum += S.u.H[ww * bins + d0 + k];
+        u32 total, run = block_excl_sum(sum, S.scan, &total);
+        if (d0 < bins) for (u32 k = 0; k < per; ++k) for (u32 ww = 0; ww < DSRC_WARPS; ++ww) { const u32 c = S.u.H[ww * bins + d0 + k]; S.u.H[ww * bins + d0 + k] = run; run += c; }
+    }
+    __syncthreads();
+    f.begin(wb);
+    for (u32 r = wb; r < we; r += 32 * SORT_U) {
+        typename F::Raw raw[SORT_U];
+#pragma unroll
+        for (int k = 0; k < SORT_U; ++k) { const u32 i = r + k * 32 + ln; raw[k] = f.ld(i, i < we); }
+#pragma unroll
+        for (int k = 0; k < SORT_U; ++k) {
+            const u32 i = r + k * 32 + ln; const bool in = i < we;
+            if (r + k * 32 >= we) break;
+            const u64 e = f.mk(raw[k], i, in);
+            const u32 d = (u32)(e >> shift) & dmask;
+            const u32 am = __ballot_sync(FULL, in);
             if (in) {
-                const u32 peers = __match_any_sync(am, dg);
-                const u32 prior = S.u.s.wcnt[w][dg];
-                rk[k] = prior + __popc(peers & ((1u << ln) - 1));
+                const u32 peers = __match_any_sync(am, d);
+                const u32 pos = H[d] + __popc(peers & lt);
                 __syncwarp(am);
-                if ((__ffs(peers) - 1) == (int)ln) S.u.s.wcnt[w][dg] = (u16)(prior + __popc(peers));
+                if ((__ffs(peers) - 1) == (int)ln) H[d] += __popc(peers);
+                dst[pos] = e;
             }
             __syncwarp();
-            if (hist_next) hist_add(hist_next, (u32)(e[k] >> (shift + 8)) & 255u, in);
         }
-        __syncthreads();
-        {   // thread = digit: turn per-warp counts into global offsets, advance the running base
-            u32 run = S.u.s.base[tid];
-#pragma unroll
-            for (int k = 0; k < DSRC_WARPS; ++k) { u32 c = S.u.s.wcnt[k][tid]; S.u.s.wcnt[k][tid] = 0; S.u.s.off[k][tid] = run; run += c; }
-            S.u.s.base[tid] = run;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < SORT_E; ++k) {
-            const u32 i = wbase + k * 32 + ln;
-            if (i < M) dst[S.u.s.off[w][(u32)(e[k] >> shift) & 255u] + rk[k]] = e[k];
-        }
-        // the next tile's wcnt writes happen after its own first barrier-free phase; off[] is only rewritten after the
-        // next __syncthreads, by which time every thread has finished the scatter above
     }
     __syncthreads();
 }
-
-#define TRIP(f, cum, tot) ((u64)(f) | ((u64)(cum) << 16) | ((u64)(tot) << 32))
 
 // A whole warp walks ONE long context run starting at sorted[a], 32 symbols per step. Within a row of 32 symbols of the
 // same context the adaptive row seen by lane l is the row at the start of the row plus 2 x (the symbols of the lanes
@@ -160,16 +210,17 @@ __device__ void sort_pass(ModelShared& S, const u64* src, u64* dst, u32 M, u32 s
 __device__ void warp_run(ModelShared& S, const u64* sorted, u64* trip, u32 M, u32 a)
 {
     const u32 N = S.cfg.alpha, limit = (1u << 16) - 2 * N, ln = lane_id(), lt = (1u << ln) - 1;
-    u32* B = S.u.l.B[warp_id()]; u32* P = S.u.l.P[warp_id()];
+    u32* B = S.u.g.l.B[warp_id()]; u32* P = S.u.g.l.P[warp_id()];
     for (u32 s = ln; s < N; s += 32) B[s] = 1;
     u32 T = N;
     const u64 key = sorted[a] >> 40;
+    u64 e_nx = a + ln < M ? sorted[a + ln] : ~0ull;
     __syncwarp();
     for (u32 row = a;; row += 32) {
-        const u32 i = row + ln;
-        const u64 e = i < M ? sorted[i] : ~0ull;
+        const u64 e = e_nx;
+        e_nx = row + 32 + ln < M ? sorted[row + 32 + ln] : ~0ull;      // next row in flight while this one is processed
         const bool valid = (e >> 40) == key;
-        const u32 vm = __ballot_sync(0xFFFFFFFFu, valid);
+        const u32 vm = __ballot_sync(FULL, valid);
         if (!vm) break;
         const u32 nv = __popc(vm);
         const u32 sym = (u32)(e >> 32) & 255u;
@@ -184,7 +235,7 @@ __device__ void warp_run(ModelShared& S, const u64* sorted, u64* trip, u32 M, u3
                     B[s] = f + 2; T += 2;
                 }
             }
-            T = __shfl_sync(0xFFFFFFFFu, T, 0);
+            T = __shfl_sync(FULL, T, 0);
             __syncwarp();
         } else {
             if (N <= 32) {
@@ -203,8 +254,8 @@ __device__ void warp_run(ModelShared& S, const u64* sorted, u64* trip, u32 M, u3
             u32 c_lt = 0, rem = vm;
             while (rem) {                              // warp-uniform: one step per distinct symbol of the row
                 const int leader = __ffs(rem) - 1;
-                const u32 gs = __shfl_sync(0xFFFFFFFFu, sym, leader);
-                const u32 gm = __shfl_sync(0xFFFFFFFFu, peers, leader);
+                const u32 gs = __shfl_sync(FULL, sym, leader);
+                const u32 gm = __shfl_sync(FULL, peers, leader);
                 if (valid && gs < sym) c_lt += __popc(gm & lt);
                 rem &= ~gm;
             }
@@ -219,65 +270,80 @@ __device__ void warp_run(ModelShared& S, const u64* sorted, u64* trip, u32 M, u3
 }
 
 // walk the context runs of the sorted array and emit the adaptive-model triple of every symbol
-// (TSymbolCoderRC<N>::EncodeSymbol / Accumulate / Rescale, src/SymbolCoderRC.h:35-48, 69-90):
-// short runs one thread each (N 16-bit counters per thread in shared memory), long runs one warp each.
-__device__ void group_scan(ModelShared& S, const u64* sorted, u64* trip, u32 M, const Workspace& ws, long long& prof_t, int prof_base)
+// (TSymbolCoderRC<N>::EncodeSymbol / Accumulate / Rescale, src/SymbolCoderRC.h:35-48, 69-90).
+// The sorted array is staged through shared memory in tiles (coalesced loads); per tile the run heads are compacted,
+// every short run (<= LONG_T symbols: no rescale possible, counters fit a byte) is walked by one thread out of shared
+// memory, and the long runs are queued (in `longq`, global) for the warp-cooperative walker.
+__device__ void group_scan(ModelShared& S, const u64* sorted, u32* longq, u64* trip, u32 M, const Workspace& ws, long long& prof_t, int prof_base)
 {
     const u32 N = S.cfg.alpha;
-    const u32 nthr = min((u32)DSRC_CTA, (u32)(CNT_BYTES / 2) / N);
-    const u32 limit = (1u << 16) - 2 * N;
-    const u32 tid = threadIdx.x;
+    const u32 nthr = N <= 64 ? (u32)DSRC_CTA : (u32)DSRC_CTA / 2;         // 16 KB of byte counters: cnt[s * nthr + tid]
+    const u32 tid = threadIdx.x, ln = lane_id(), lt = (1u << ln) - 1;
+    u64* tile = S.u.g.t.tile; u16* heads = S.u.g.t.heads; u8* cnt = S.u.g.t.cnt + tid;
     if (tid == 0) S.n_long = 0;
-    __syncthreads();
-    if (tid < nthr) {
-        u16* cnt = S.u.cnt + tid;                        // counter of symbol s at cnt[s * nthr]
-        for (u32 i = tid; i < M; i += nthr) {
-            const u64 e0 = sorted[i];
-            const u64 key = e0 >> 40;
-            if (i > 0 && (sorted[i - 1] >> 40) == key) continue;     // not a run head
-            u64 nx = (i + 1 < M) ? sorted[i + 1] : ~0ull;             // ~0 is never a key (contexts have <= 21 bits)
-            if ((nx >> 40) != key) {                      // fresh row: all ones
-                const u32 s = (u32)(e0 >> 32) & 255u;
-                trip[(u32)e0] = TRIP(1, s, N);
-                continue;
+    for (u32 t0 = 0; t0 < M; t0 += SCAN_TILE) {
+        const u32 n = min((u32)SCAN_TILE, M - t0), avail = min(n + SCAN_LOOK, M - t0);
+        __syncthreads();
+        if (tid == 0) S.n_heads = 0;
+        for (u32 p = tid; p < avail; p += DSRC_CTA) tile[p] = sorted[t0 + p];
+        const u32 prevkey = t0 ? (u32)(sorted[t0 - 1] >> 40) : 0xFFFFFFFFu;
+        __syncthreads();
+        for (u32 p0 = 0; p0 < n; p0 += DSRC_CTA) {
+            const u32 p = p0 + tid; const bool in = p < n;
+            const u64 e = in ? tile[p] : ~0ull;
+            const u32 key = (u32)(e >> 40);
+            bool push = false;
+            if (in && key != (p ? (u32)(tile[p - 1] >> 40) : prevkey)) {
+                const u32 nk = p + 1 < avail ? (u32)(tile[p + 1] >> 40) : 0xFFFFFFFFu;
+                if (nk != key) trip[(u32)e] = TRIP(1, (u32)(e >> 32) & 255u, N);          // run of one: fresh row, all ones
+                else if (p + LONG_T < avail && (u32)(tile[p + LONG_T] >> 40) == key) longq[atomicAdd(&S.n_long, 1u)] = t0 + p;
+                else push = true;
             }
-            if (i + LONG_T < M && (sorted[i + LONG_T] >> 40) == key) {
-                const u32 slot = atomicAdd(&S.n_long, 1u);
-                if (slot < LONGQ_MAX) { S.longq[slot] = i; continue; }
+            const u32 m = __ballot_sync(FULL, push);
+            if (m) {
+                u32 base = 0;
+                const int leader = __ffs(m) - 1;
+                if ((int)ln == leader) base = atomicAdd(&S.n_heads, (u32)__popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                if (push) heads[base + __popc(m & lt)] = (u16)p;
             }
-            for (u32 s = 0; s < N; ++s) cnt[s * nthr] = 1;
-            u32 tot = N, k = i;
-            u64 e = e0;
-            for (;;) {
-                const u32 s = (u32)(e >> 32) & 255u;
-                if (tot >= limit) {                       // Rescale: stats[i] -= stats[i] >> 1
-                    tot = 0;
-                    for (u32 q = 0; q < N; ++q) { u32 c = cnt[q * nthr]; c -= c >> 1; cnt[q * nthr] = (u16)c; tot += c; }
-                }
-                const u32 f = cnt[s * nthr];
-                u32 cum = 0;
-                if (s * 2 <= N) { for (u32 q = 0; q < s; ++q) cum += cnt[q * nthr]; }
-                else { u32 hi = 0; for (u32 q = s; q < N; ++q) hi += cnt[q * nthr]; cum = tot - hi; }
-                trip[(u32)e] = TRIP(f, cum, tot);
-                cnt[s * nthr] = (u16)(f + 2); tot += 2;
-                e = nx; ++k;
-                if ((e >> 40) != key) break;
-                nx = (k + 1 < M) ? sorted[k + 1] : ~0ull;
+        }
+        __syncthreads();
+        const u32 nh = S.n_heads;
+        if (tid < nthr) {
+            for (u32 h = tid; h < nh; h += nthr) {
+                u32 p = heads[h];
+                u64 e = tile[p];
+                const u32 key = (u32)(e >> 40);
+                for (u32 s = 0; s < N; ++s) cnt[s * nthr] = 1;
+                u32 tot = N;
+                do {
+                    const u32 s = (u32)(e >> 32) & 255u;
+                    const u32 f = cnt[s * nthr];
+                    u32 cum = 0;
+                    if (s * 2 <= N) { for (u32 q = 0; q < s; ++q) cum += cnt[q * nthr]; }
+                    else { u32 hi = 0; for (u32 q = s; q < N; ++q) hi += cnt[q * nthr]; cum = tot - hi; }
+                    trip[(u32)e] = TRIP(f, cum, tot);
+                    cnt[s * nthr] = (u8)(f + 2); tot += 2;
+                    if (++p >= avail) break;
+                    e = tile[p];
+                } while ((u32)(e >> 40) == key);
             }
         }
     }
     __syncthreads();
-    PROF_MARK(prof_base + 2);
-    const u32 n_long = min(S.n_long, (u32)LONGQ_MAX);
-    for (u32 r = warp_id(); r < n_long; r += DSRC_WARPS) warp_run(S, sorted, trip, M, S.longq[r]);
-    __syncthreads();
     PROF_MARK(prof_base + 3);
+    const u32 n_long = S.n_long;
+    for (u32 r = warp_id(); r < n_long; r += DSRC_WARPS) warp_run(S, sorted, trip, M, longq[r]);
+    __syncthreads();
+    PROF_MARK(prof_base + 4);
 }
 
 template <bool QUALITY>
 __global__ void __launch_bounds__(DSRC_CTA) k_model(Workspace ws, u64 arena_stride)
 {
     __shared__ ModelShared S;
+    TabShared& TS = S.u.tab;
     const u32 tid = threadIdx.x;
     u64* bufA = ws.elem_a + (u64)blockIdx.x * arena_stride;
     u64* bufB = ws.elem_b + (u64)blockIdx.x * arena_stride;
@@ -311,67 +377,55 @@ __global__ void __launch_bounds__(DSRC_CTA) k_model(Workspace ws, u64 arena_stri
             if (S.M > arena_stride) { S.ok = 0; st.status = ST_OVERFLOW; }
         }
         if (QUALITY) S.rank[tid] = st.qrank[tid];
-        S.u.s.hist[0][tid] = 0;
         __syncthreads();
         if (!S.ok || S.M == 0) continue;
         const ModelCfg cfg = S.cfg;
         const u32 M = S.M;
-        const u32 passes = (cfg.key_bits + 7) / 8;
+        const u32 passes = (cfg.key_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
+        const u32 pbits = (cfg.key_bits + passes - 1) / passes;
 
-        // ---- keys: (ctx << 40) | (sym << 32) | index
+        u64* const trip = (QUALITY ? ws.trip_q : ws.trip_d) + d.sym_base;
+        u8* pc = (u8*)bufB;
         if (QUALITY) {
-            const u8* q = ws.qcat + d.sym_base;
+            // position bucket of every symbol (TTranslationalQualityEncoder::Encode :307), parked in the idle sort buffer
             const RecArrays& R = ws.rec;
-            const u32 h = cfg.sym_order / 2, so = cfg.sym_order, bits = cfg.bits;
             for (u32 r = warp_id(); r < st.n_rec; r += DSRC_WARPS) {
                 const u32 len = R.qua_len[d.rec_base + r], qo = R.qcat_off[d.rec_base + r];
-                for (u32 j0 = 0; j0 < len; j0 += 32) {
-                    const u32 j = j0 + lane_id(); const bool in = j < len;
-                    u64 el = 0; u32 ctx = 0;
-                    if (in) {
-                        const u32 i = qo + j;
-                        u32 y[6];                                  // y[k] = symbol k steps back (0 before the block start)
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) y[k] = (i >= (u32)k) ? S.rank[q[i - k]] : 0u;
-                        // hash slots (QualityEncoder.h:77-94): raw below slot h, pairwise means from slot h on
-                        u32 hash = 0;
-                        if (so == 1) hash = y[1];
-                        else for (u32 t = 0; t < so; ++t) {
-                            u32 v = t < h ? y[t + 1] : ((y[t + 1] + y[t + 2]) >> 1);
-                            hash |= v << (t * bits);
-                        }
-                        const u32 pctx = j * cfg.rescale / len;     // TTranslationalQualityEncoder::Encode :307
-                        ctx = (hash << bits) | pctx;
-                        el = ((u64)ctx << 40) | ((u64)y[0] << 32) | i;
-                        bufA[i] = el;
-                    }
-                    hist_add(S.u.s.hist[0], ctx & 255u, in);
-                }
+                for (u32 j = lane_id(); j < len; j += 32) pc[qo + j] = (u8)(j * cfg.rescale / len);
             }
-        } else {
-            const u8* sq = ws.dcat + d.sym_base;
-            const u32 bits = cfg.bits, ord = cfg.ord;
-            for (u32 i0 = 0; i0 < M; i0 += DSRC_CTA) {
-                const u32 i = i0 + tid; const bool in = i < M;
-                u32 ctx = 0;
-                if (in) {
-                    for (u32 t = 0; t < ord; ++t) { u32 v = (i >= t + 1) ? sq[i - t - 1] : 0u; ctx |= (v & ((1u << bits) - 1)) << (t * bits); }
-                    bufA[i] = ((u64)ctx << 40) | ((u64)sq[i] << 32) | i;
-                }
-                hist_add(S.u.s.hist[0], ctx & 255u, in);
-            }
+            __syncthreads();
         }
-        __syncthreads();
+        if (cfg.alpha <= 16 && ws.tab) {
+            // ---- tile/table engine (model_tab.cuh)
+            u8* tab = ws.tab + (u64)blockIdx.x * ws.tab_stride;
+            if (QUALITY) {
+                FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M;
+                tab_engine<16>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 16);
+            } else {
+                FetchD f; f.sq = ws.dcat + d.sym_base; f.ord = cfg.ord; f.bits = cfg.bits; f.prev = 0; f.M = M;
+                if (cfg.alpha == 4) tab_engine<4>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 24);
+                else tab_engine<8>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 24);
+            }
+            continue;
+        }
+        // ---- sort engine: first pass straight from the symbols (contexts are a pure function of the input), then passes over elements
+        if (QUALITY) {
+            FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M;
+            sort_pass(S, f, bufA, M, 40, pbits);
+        } else {
+            FetchD f; f.sq = ws.dcat + d.sym_base; f.ord = cfg.ord; f.bits = cfg.bits; f.prev = 0; f.M = M;
+            sort_pass(S, f, bufA, M, 40, pbits);
+        }
         PROF_MARK(prof_base + 0);
-        // ---- stable LSD radix sort by context
         u64* src = bufA; u64* dst = bufB;
-        for (u32 p = 0; p < passes; ++p) {
-            sort_pass(S, src, dst, M, 40 + 8 * p, S.u.s.hist[p & 1], (p + 1 < passes) ? S.u.s.hist[(p + 1) & 1] : nullptr);
+        for (u32 p = 1; p < passes; ++p) {
+            FetchSorted f; f.src = src;
+            sort_pass(S, f, dst, M, 40 + p * pbits, pbits);
             u64* t = src; src = dst; dst = t;
         }
         PROF_MARK(prof_base + 1);
         // ---- adaptive statistics per context run
-        group_scan(S, src, (QUALITY ? ws.trip_q : ws.trip_d) + d.sym_base, M, ws, prof_t, prof_base);
+        group_scan(S, src, (u32*)dst, trip, M, ws, prof_t, prof_base);
     }
 }
 
