@@ -10,7 +10,7 @@ LIB = os.path.join(HERE, "libdsrc_b200.so")
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(HERE, "csrc", s) for s in SRCS]
-    deps = srcs + [os.path.join(HERE, "csrc", h) for h in ("common.cuh", "kernels.h", "huff.cuh")] + \
+    deps = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + \
         [os.path.join(os.path.dirname(HERE), "include", "dsrc_b200.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
         return LIB

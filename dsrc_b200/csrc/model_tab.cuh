@@ -12,31 +12,45 @@
 
 #define TT 2048                               // symbols per tile
 #define TT_SHIFT 11
+#define TAB_C1 6
+#define TAB_LONG 24                           // groups longer than this take a whole warp
 
 struct TabShared {
     u32 el[2][TT];                            // (ctx << 11) | position in tile, ping-pong of the in-tile sort
     u8 sym[TT];
     union { u64 trip[TT]; u16 H[DSRC_WARPS << 10]; } x;   // triple staging / sort counters (never live together)
+    // group heads by size class so that the lanes of a warp walk groups of similar length:
+    // class 0: 1..2 symbols, class 1: 3..TAB_C1, class 2: TAB_C1+1..TAB_LONG; longer groups take a whole warp
     u16 heads[TT];
-    u16 longs[TT / LONG_T + 2];
+    u16 heads1[TT / 3 + 2];
+    u16 heads2[TT / (TAB_C1 + 1) + 2];
+    u16 longs[TT / (TAB_LONG + 1) + 2];
     u32 B[DSRC_WARPS][16], P[DSRC_WARPS][16];
-    u32 n_heads, n_long, n_touched;
+    u32 n_heads[3], n_long, n_touched;
 };
 
-__device__ __forceinline__ void tile_sort_pass(TabShared& S, u32* scan, const u32* src, u32* dst, u32 n, u32 shift, u32 bits)
+// lanes holding the same `bits`-wide digit (replaces match.any, whose cost grows with the number of distinct values)
+__device__ __forceinline__ u32 match_bits(u32 d, u32 bits, u32 active)
+{
+    u32 peers = active;
+    for (u32 k = 0; k < bits; ++k) { const u32 m = __ballot_sync(FULL, (d >> k) & 1u); peers &= ((d >> k) & 1u) ? m : ~m; }
+    return peers;
+}
+
+template <int BITS>
+__device__ __forceinline__ void tile_sort_pass_t(TabShared& S, u32* scan, const u32* src, u32* dst, u32 n, u32 shift)
 {
     const u32 tid = threadIdx.x, w = warp_id(), ln = lane_id(), lt = (1u << ln) - 1;
-    const u32 bins = 1u << bits, dmask = bins - 1;
+    const u32 bins = 1u << BITS, dmask = bins - 1;
     const u32 wb = min(n, w * (TT / DSRC_WARPS)), we = min(n, wb + TT / DSRC_WARPS);
     u16* H = S.x.H + w * bins;
-    for (u32 i = tid; i < DSRC_WARPS * bins; i += DSRC_CTA) S.x.H[i] = 0;
+    u32* H32 = (u32*)H;
+    for (u32 i = tid; i < DSRC_WARPS * bins / 2; i += DSRC_CTA) ((u32*)S.x.H)[i] = 0;
     __syncthreads();
+    // per-warp digit histogram: packed 16-bit counters bumped with 32-bit shared atomics (counts <= 256, no carry)
     for (u32 r = wb; r < we; r += 32) {
-        const u32 i = r + ln; const bool in = i < we;
-        const u32 d = in ? (src[i] >> shift) & dmask : 0u;
-        const u32 am = __ballot_sync(FULL, in);
-        if (in) { const u32 peers = __match_any_sync(am, d); if ((__ffs(peers) - 1) == (int)ln) H[d] += (u16)__popc(peers); }
-        __syncwarp();
+        const u32 i = r + ln;
+        if (i < we) { const u32 d = (src[i] >> shift) & dmask; atomicAdd(&H32[d >> 1], 1u << ((d & 1) * 16)); }
     }
     __syncthreads();
     {
@@ -51,17 +65,29 @@ __device__ __forceinline__ void tile_sort_pass(TabShared& S, u32* scan, const u3
         const u32 i = r + ln; const bool in = i < we;
         const u32 e = in ? src[i] : 0u;
         const u32 d = (e >> shift) & dmask;
-        const u32 am = __ballot_sync(FULL, in);
+        u32 peers = __ballot_sync(FULL, in);
+#pragma unroll
+        for (int k = 0; k < BITS; ++k) { const u32 m = __ballot_sync(FULL, (d >> k) & 1u); peers &= ((d >> k) & 1u) ? m : ~m; }
+        const u32 pos = in ? H[d] + __popc(peers & lt) : 0u;
+        __syncwarp();
         if (in) {
-            const u32 peers = __match_any_sync(am, d);
-            const u32 pos = H[d] + __popc(peers & lt);
-            __syncwarp(am);
             if ((__ffs(peers) - 1) == (int)ln) H[d] += (u16)__popc(peers);
             dst[pos] = e;
         }
         __syncwarp();
     }
     __syncthreads();
+}
+__device__ __forceinline__ void tile_sort_pass(TabShared& S, u32* scan, const u32* src, u32* dst, u32 n, u32 shift, u32 bits)
+{
+    switch (bits) {
+    case 3: tile_sort_pass_t<3>(S, scan, src, dst, n, shift); break;
+    case 6: tile_sort_pass_t<6>(S, scan, src, dst, n, shift); break;
+    case 7: tile_sort_pass_t<7>(S, scan, src, dst, n, shift); break;
+    case 8: tile_sort_pass_t<8>(S, scan, src, dst, n, shift); break;
+    case 9: tile_sort_pass_t<9>(S, scan, src, dst, n, shift); break;
+    default: tile_sort_pass_t<10>(S, scan, src, dst, n, shift); break;       // a wider digit than needed only costs idle bins
+    }
 }
 
 // counter k of a row held as N/2 packed u16 pairs
@@ -107,9 +133,11 @@ template <int N>
 __device__ void tab_short_groups(TabShared& S, const u32* sorted, u32 n, u8* tab, u32* touched)
 {
     const u32 limit = (1u << 16) - 2 * N;
-    const u32 nh = S.n_heads;
+    for (int cls = 0; cls < 3; ++cls) {
+    const u16* list = cls == 0 ? S.heads : cls == 1 ? S.heads1 : S.heads2;
+    const u32 nh = S.n_heads[cls];
     for (u32 h = threadIdx.x; h < nh; h += DSRC_CTA) {
-        u32 p = S.heads[h];
+        u32 p = list[h];
         u32 e = sorted[p];
         const u32 key = e >> TT_SHIFT;
         u8* rowp = tab + (u64)key * (2 * N);
@@ -126,6 +154,7 @@ __device__ void tab_short_groups(TabShared& S, const u32* sorted, u32 n, u8* tab
             e = sorted[p];
         } while ((e >> TT_SHIFT) == key);
         R.store(rowp);
+    }
     }
 }
 
@@ -207,7 +236,7 @@ __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8
     for (u32 t0 = 0; t0 < M; t0 += TT) {
         const u32 n = min((u32)TT, M - t0);
         __syncthreads();
-        if (tid == 0) { S.n_heads = 0; S.n_long = 0; }
+        if (tid == 0) { S.n_heads[0] = S.n_heads[1] = S.n_heads[2] = 0; S.n_long = 0; }
         // contexts of the tile, in original order
         {
             const u32 wb = w * (TT / DSRC_WARPS);
@@ -228,22 +257,28 @@ __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8
         for (u32 ps = 0; ps < passes; ++ps) { tile_sort_pass(S, scan, S.el[cur], S.el[cur ^ 1], n, TT_SHIFT + ps * pbits, pbits); cur ^= 1; }
         const u32* sorted = S.el[cur];
         PROF_MARK(pb + 1);
-        // group heads
+        // group heads, by size class
         for (u32 p0 = 0; p0 < n; p0 += DSRC_CTA) {
             const u32 p = p0 + tid; const bool in = p < n;
             const u32 key = in ? sorted[p] >> TT_SHIFT : 0u;
-            bool push = false;
+            int cls = -1;
             if (in && (p == 0 || (sorted[p - 1] >> TT_SHIFT) != key)) {
-                if (p + LONG_T < n && (sorted[p + LONG_T] >> TT_SHIFT) == key) S.longs[atomicAdd(&S.n_long, 1u)] = (u16)p;
-                else push = true;
+                if (!(p + 2 < n && (sorted[p + 2] >> TT_SHIFT) == key)) cls = 0;
+                else if (!(p + TAB_C1 < n && (sorted[p + TAB_C1] >> TT_SHIFT) == key)) cls = 1;
+                else if (!(p + TAB_LONG < n && (sorted[p + TAB_LONG] >> TT_SHIFT) == key)) cls = 2;
+                else S.longs[atomicAdd(&S.n_long, 1u)] = (u16)p;
             }
-            const u32 m = __ballot_sync(FULL, push);
-            if (m) {
-                u32 base = 0;
-                const int leader = __ffs(m) - 1;
-                if ((int)ln == leader) base = atomicAdd(&S.n_heads, (u32)__popc(m));
-                base = __shfl_sync(FULL, base, leader);
-                if (push) S.heads[base + __popc(m & lt)] = (u16)p;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const u32 m = __ballot_sync(FULL, cls == c);
+                if (m) {
+                    u32 base = 0;
+                    const int leader = __ffs(m) - 1;
+                    if ((int)ln == leader) base = atomicAdd(&S.n_heads[c], (u32)__popc(m));
+                    base = __shfl_sync(FULL, base, leader);
+                    u16* list = c == 0 ? S.heads : c == 1 ? S.heads1 : S.heads2;
+                    if (cls == c) list[base + __popc(m & lt)] = (u16)p;
+                }
             }
         }
         __syncthreads();

@@ -163,8 +163,8 @@ __device__ void sort_pass(ModelShared& S, F f, u64* dst, u32 M, u32 shift, u32 b
             if (r + k * 32 >= we) break;
             const u64 e = f.mk(raw[k], i, in);
             const u32 d = (u32)(e >> shift) & dmask;
-            const u32 am = __ballot_sync(FULL, in);
-            if (in) { const u32 peers = __match_any_sync(am, d); if ((__ffs(peers) - 1) == (int)ln) H[d] += __popc(peers); }
+            const u32 peers = match_bits(d, bits, __ballot_sync(FULL, in));
+            if (in && (__ffs(peers) - 1) == (int)ln) H[d] += __popc(peers);
             __syncwarp();
         }
     }
@@ -188,11 +188,10 @@ __device__ void sort_pass(ModelShared& S, F f, u64* dst, u32 M, u32 shift, u32 b
             if (r + k * 32 >= we) break;
             const u64 e = f.mk(raw[k], i, in);
             const u32 d = (u32)(e >> shift) & dmask;
-            const u32 am = __ballot_sync(FULL, in);
+            const u32 peers = match_bits(d, bits, __ballot_sync(FULL, in));
+            const u32 pos = in ? H[d] + __popc(peers & lt) : 0u;
+            __syncwarp();
             if (in) {
-                const u32 peers = __match_any_sync(am, d);
-                const u32 pos = H[d] + __popc(peers & lt);
-                __syncwarp(am);
                 if ((__ffs(peers) - 1) == (int)ln) H[d] += __popc(peers);
                 dst[pos] = e;
             }
@@ -340,7 +339,7 @@ __device__ void group_scan(ModelShared& S, const u64* sorted, u32* longq, u64* t
 }
 
 template <bool QUALITY>
-__global__ void __launch_bounds__(DSRC_CTA) k_model(Workspace ws, u64 arena_stride)
+__global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_stride)
 {
     __shared__ ModelShared S;
     TabShared& TS = S.u.tab;
