@@ -114,6 +114,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (BASELINE configs[1]: 50 M)")
     ap.add_argument("--profile", type=int, default=0)
+    ap.add_argument("--inflight", type=int, default=4096, help="blocks per batch (one batch per stream slot)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -175,7 +176,7 @@ def main():
     ds = _lib.Dataset(33, 0, 0)
     cs = _lib.Settings(DNA_ORDER, QUA_ORDER, 0, 0, 0)
     ctx = C.c_void_p()
-    rc = L.dsrcgpu_create(C.byref(ctx), local_rank, C.byref(ds), C.byref(cs), BLOCK_BYTES, 4096)
+    rc = L.dsrcgpu_create(C.byref(ctx), local_rank, C.byref(ds), C.byref(cs), BLOCK_BYTES, args.inflight)
     if rc:
         raise SystemExit("dsrcgpu_create failed: %d" % rc)
 

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DSRCGPU_E_CUDA; } } while (0)
 
@@ -32,30 +33,51 @@ struct DevBuf {
 enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_NUM };
 static const char* K_NAMES[K_NUM] = {"count_lines", "parse", "preprocess", "tags", "model_quality", "model_dna", "rc_encode",
                                      "q0_quality", "d0_dna", "meta_sizes", "gather", "decode"};
+#define MAX_SLOTS 4
+
+// One in-flight batch of blocks: its own stream, workspace and pinned staging. The scheduler keeps several slots busy so
+// that the copies of one batch, the parallel kernels of the next and the serial range-coder chains of a third overlap.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
+    DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
+    DevBuf elem_a, elem_b, tagpool, q0_arena, tab;          // per-CTA arenas of the persistent kernels
+    BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
+    cudaEvent_t ev_results = nullptr, ev_sizes = nullptr;
+    bool busy = false; u32 first = 0, cnt = 0, batch = 0;
+    std::vector<u64> offs;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
+    void release()
+    {
+        DevBuf* bufs[] = {&in, &desc, &state, &result, &probe, &lines, &qcat, &dcat, &trip_q, &trip_d, &ftab, &streams, &out, &r_title_off, &r_seq_off,
+                          &r_qua_off, &r_title_len, &r_qua_len, &r_dna_len, &r_trunc_len, &r_qcat_off, &r_dcat_off, &elem_a, &elem_b, &tagpool, &q0_arena, &tab};
+        for (DevBuf* b : bufs) b->release();
+        if (h_desc) cudaFreeHost(h_desc);
+        if (h_result) cudaFreeHost(h_result);
+        if (h_probe) cudaFreeHost(h_probe);
+        h_desc = nullptr; h_result = nullptr; h_probe = nullptr; h_cap = 0;
+        if (ev_results) cudaEventDestroy(ev_results);
+        if (ev_sizes) cudaEventDestroy(ev_sizes);
+        if (stream) cudaStreamDestroy(stream);
+        ev_results = ev_sizes = nullptr; stream = nullptr;
+    }
+};
 
 struct dsrcgpu_ctx {
     int device = 0, sms = 148;
     dsrcgpu_dataset_t ds{};
     dsrcgpu_settings_t cs{};
     u32 max_block = 0, max_inflight = 0;
-    cudaStream_t stream = nullptr;
     std::string err;
-    // batch-wide device buffers
-    DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
-    DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
-    // persistent per-CTA arenas
-    DevBuf elem_a, elem_b, tagpool, dec_arena, q0_arena, prof, tab;
+    Slot slots[MAX_SLOTS]; int n_slots = 1;
+    DevBuf prof, cursor, dec_arena;
     u64 tab_stride = 0;
-    bool phase_prof = false;
     u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0; u32 q0_ctas = 0; u64 q0_stride = 0;
-    // pinned host staging
-    BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
     // per-kernel timing
-    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
     std::vector<cudaEvent_t> ev_pool;
     float k_ms[K_NUM]; u32 k_launches[K_NUM];
     cudaEvent_t call_a = nullptr, call_b = nullptr; float call_ms = 0;
-    bool profiling = true;
+    bool profiling = true, phase_prof = false;
 };
 
 static cudaEvent_t get_event(dsrcgpu_ctx* ctx)
@@ -64,22 +86,22 @@ static cudaEvent_t get_event(dsrcgpu_ctx* ctx)
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct KTimer {
-    dsrcgpu_ctx* ctx; int k; cudaEvent_t a = nullptr, b = nullptr;
-    KTimer(dsrcgpu_ctx* c, int kid) : ctx(c), k(kid)
+    dsrcgpu_ctx* ctx; Slot* sl; int k; cudaEvent_t a = nullptr, b = nullptr;
+    KTimer(dsrcgpu_ctx* c, Slot* s, int kid) : ctx(c), sl(s), k(kid)
     {
         ctx->k_launches[k]++;
-        if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+        if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, sl->stream); }
     }
-    ~KTimer() { if (ctx->profiling) { cudaEventRecord(b, ctx->stream); ctx->ev_used.push_back({k, {a, b}}); } }
+    ~KTimer() { if (ctx->profiling) { cudaEventRecord(b, sl->stream); sl->ev_used.push_back({k, {a, b}}); } }
 };
-static void collect_times(dsrcgpu_ctx* ctx)
+static void collect_times(dsrcgpu_ctx* ctx, Slot* sl)
 {
-    for (auto& u : ctx->ev_used) {
+    for (auto& u : sl->ev_used) {
         float ms = 0; cudaEventElapsedTime(&ms, u.second.first, u.second.second);
         ctx->k_ms[u.first] += ms;
         ctx->ev_pool.push_back(u.second.first); ctx->ev_pool.push_back(u.second.second);
     }
-    ctx->ev_used.clear();
+    sl->ev_used.clear();
 }
 
 extern "C" const char* dsrcgpu_last_error(dsrcgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
@@ -100,16 +122,29 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DSRCGPU_E_CUDA; }
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DSRCGPU_E_CUDA; }
     if (max_inflight_blocks == 0) {
-        u64 n = (1ull << 30) / max_block_bytes;          // ~1 GiB of FASTQ per batch
+        u64 n = (512ull << 20) / max_block_bytes;          // ~0.5 GiB of FASTQ per batch
         max_inflight_blocks = (u32)std::min<u64>(std::max<u64>(n, 1), 4096);
     }
     ctx->max_inflight = max_inflight_blocks;
-    // persistent CTAs: 4 per SM unless the sort arenas (2 x 8 B x block/2 entries each) would exceed ~16 GiB
+    // batches in flight (streams): 3 by default -- copies, parallel kernels and the range-coder chains of different batches overlap
+    int ns = 3;
+    if (const char* e = getenv("DSRCGPU_SLOTS")) ns = atoi(e);
+    ctx->n_slots = std::max(1, std::min(ns, (int)MAX_SLOTS));
+    for (int i = 0; i < ctx->n_slots; ++i) {
+        Slot& sl = ctx->slots[i];
+        if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sl.ev_results, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sl.ev_sizes, cudaEventDisableTiming) != cudaSuccess) {
+            for (int k = 0; k <= i; ++k) ctx->slots[k].release();
+            delete ctx; return DSRCGPU_E_CUDA;
+        }
+    }
+    // persistent model CTAs: 3 per SM (the fourth CTA slot of every SM is left to the range-coder chains of the batch
+    // before), fewer if the sort arenas (2 x 8 B x block/2 entries each) would exceed ~8 GiB per slot
     ctx->model_stride = (u64)max_block_bytes / 2 + 64;
     u64 per_cta = ctx->model_stride * 8 * 2;
-    u64 ctas = std::min<u64>((u64)ctx->sms * 4, std::max<u64>(1, (16ull << 30) / per_cta));
+    u64 ctas = std::min<u64>((u64)ctx->sms * (ctx->n_slots > 1 ? 3 : 4), std::max<u64>(1, (8ull << 30) / per_cta));
     ctas = std::min<u64>(ctas, max_inflight_blocks);
     ctx->model_ctas = (u32)ctas;
     {   // adaptive-row tables of the tile/table model engine: rows of 2N bytes, one table per persistent CTA
@@ -120,7 +155,7 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     }
     ctx->tag_ctas = (u32)std::min<u64>((u64)ctx->sms * 4, max_inflight_blocks);
     ctx->q0_stride = q0_arena_bytes(max_block_bytes);
-    ctx->q0_ctas = (u32)std::min<u64>(std::min<u64>((u64)ctx->sms * 2, max_inflight_blocks), std::max<u64>(1, (16ull << 30) / ctx->q0_stride));
+    ctx->q0_ctas = (u32)std::min<u64>(std::min<u64>((u64)ctx->sms * 2, max_inflight_blocks), std::max<u64>(1, (8ull << 30) / ctx->q0_stride));
     *out = ctx;
     return DSRCGPU_OK;
 }
@@ -129,16 +164,11 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->in, &ctx->desc, &ctx->state, &ctx->result, &ctx->probe, &ctx->lines, &ctx->qcat, &ctx->dcat, &ctx->trip_q, &ctx->trip_d,
-                      &ctx->ftab, &ctx->streams, &ctx->out, &ctx->r_title_off, &ctx->r_seq_off, &ctx->r_qua_off, &ctx->r_title_len, &ctx->r_qua_len,
-                      &ctx->r_dna_len, &ctx->r_trunc_len, &ctx->r_qcat_off, &ctx->r_dcat_off, &ctx->elem_a, &ctx->elem_b, &ctx->tagpool, &ctx->dec_arena, &ctx->q0_arena, &ctx->prof, &ctx->tab};
-    for (DevBuf* b : bufs) b->release();
-    if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
-    if (ctx->h_result) cudaFreeHost(ctx->h_result);
-    if (ctx->h_probe) cudaFreeHost(ctx->h_probe);
+    for (int i = 0; i < ctx->n_slots; ++i) { if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream); ctx->slots[i].release(); }
+    ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->call_a) cudaEventDestroy(ctx->call_a);
+    if (ctx->call_b) cudaEventDestroy(ctx->call_b);
     delete ctx;
 }
 
@@ -166,17 +196,17 @@ extern "C" int dsrcgpu_last_kernel_times(dsrcgpu_ctx* ctx, const char** names, f
     return n;
 }
 
-static int ensure_host(dsrcgpu_ctx* ctx, u32 n)
+static int ensure_host(dsrcgpu_ctx* ctx, Slot& sl, u32 n)
 {
-    if (n <= ctx->h_cap) return DSRCGPU_OK;
-    if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
-    if (ctx->h_result) cudaFreeHost(ctx->h_result);
-    if (ctx->h_probe) cudaFreeHost(ctx->h_probe);
-    ctx->h_desc = nullptr; ctx->h_result = nullptr; ctx->h_probe = nullptr; ctx->h_cap = 0;
-    CK(cudaHostAlloc((void**)&ctx->h_desc, sizeof(BlockDesc) * n, cudaHostAllocDefault));
-    CK(cudaHostAlloc((void**)&ctx->h_result, sizeof(BlockResult) * n, cudaHostAllocDefault));
-    CK(cudaHostAlloc((void**)&ctx->h_probe, sizeof(BlockProbe) * n, cudaHostAllocDefault));
-    ctx->h_cap = n;
+    if (n <= sl.h_cap) return DSRCGPU_OK;
+    if (sl.h_desc) cudaFreeHost(sl.h_desc);
+    if (sl.h_result) cudaFreeHost(sl.h_result);
+    if (sl.h_probe) cudaFreeHost(sl.h_probe);
+    sl.h_desc = nullptr; sl.h_result = nullptr; sl.h_probe = nullptr; sl.h_cap = 0;
+    CK(cudaHostAlloc((void**)&sl.h_desc, sizeof(BlockDesc) * n, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&sl.h_result, sizeof(BlockResult) * n, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&sl.h_probe, sizeof(BlockProbe) * n, cudaHostAllocDefault));
+    sl.h_cap = n;
     return DSRCGPU_OK;
 }
 
@@ -195,46 +225,48 @@ static int status_to_error(dsrcgpu_ctx* ctx, u32 status, u32 blk)
     return code;
 }
 
-// one batch of blocks through the encode pipeline. d_in/d_out are device pointers.
-static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, const u32* blk_len, const u32* blk_tagcap, u32 n,
-                        u8* d_out, u64 out_base, u64 out_cap, u64* out_end)
+// Enqueues one batch of blocks on its slot's stream: layout probe (one short host sync), then every per-block kernel and the
+// result read-back, all asynchronous. d_in / d_out are device pointers; with `cursor` the dense output continues where the
+// previous batch ended (device-resident output), else the batch starts at out_base of its own staging buffer.
+static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* blk_len, const u32* blk_tagcap, u32 n,
+                         u8* d_out, u64 out_base, u64 out_cap, u64* cursor, cudaEvent_t wait_sizes)
 {
-    int rc = ensure_host(ctx, n);
+    int rc = ensure_host(ctx, sl, n);
     if (rc) return rc;
-    cudaStream_t s = ctx->stream;
-    CK(ctx->desc.ensure(sizeof(BlockDesc) * n));
-    CK(ctx->state.ensure(sizeof(BlockState) * n));
-    CK(ctx->result.ensure(sizeof(BlockResult) * n));
-    CK(ctx->probe.ensure(sizeof(BlockProbe) * n));
-    BlockDesc* hd = ctx->h_desc;
+    cudaStream_t s = sl.stream;
+    CK(sl.desc.ensure(sizeof(BlockDesc) * n));
+    CK(sl.state.ensure(sizeof(BlockState) * n));
+    CK(sl.result.ensure(sizeof(BlockResult) * n));
+    CK(sl.probe.ensure(sizeof(BlockProbe) * n));
+    BlockDesc* hd = sl.h_desc;
     for (u32 i = 0; i < n; ++i) {
         memset(&hd[i], 0, sizeof(BlockDesc));
-        hd[i].in_off = in_off[i]; hd[i].in_len = blk_len[i];
+        hd[i].in_off = sl.offs[i]; hd[i].in_len = blk_len[i];
         hd[i].tag_cap = blk_tagcap ? blk_tagcap[i] : 0xFFFFFFFFu;
         if (blk_len[i] == 0 || blk_len[i] > ctx->max_block) { ctx->err = "block length 0 or above max_block_bytes"; return DSRCGPU_E_ARG; }
     }
     Workspace ws{};
-    ws.in = d_in; ws.desc = (const BlockDesc*)ctx->desc.p; ws.state = (BlockState*)ctx->state.p;
-    ws.result = (BlockResult*)ctx->result.p; ws.probe = (BlockProbe*)ctx->probe.p;
+    ws.in = d_in; ws.desc = (const BlockDesc*)sl.desc.p; ws.state = (BlockState*)sl.state.p;
+    ws.result = (BlockResult*)sl.result.p; ws.probe = (BlockProbe*)sl.probe.p;
     ws.n_blocks = n; ws.qoff = ctx->ds.quality_offset; ws.plus_rep = ctx->ds.plus_repetition;
     ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order;
     ws.out = d_out; ws.out_cap = out_cap;
     if (ctx->phase_prof) { if (!ctx->prof.p) { CK(ctx->prof.ensure(64 * 8)); CK(cudaMemsetAsync(ctx->prof.p, 0, 64 * 8, s)); } ws.prof = (u64*)ctx->prof.p; }
 
     // pass 1: count lines / fields so the batch can be laid out exactly
-    CK(cudaMemcpyAsync(ctx->desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
-    { KTimer t(ctx, K_COUNT); launch_count_lines(ws, s); }
-    CK(cudaMemcpyAsync(ctx->h_probe, ctx->probe.p, sizeof(BlockProbe) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    { KTimer t(ctx, &sl, K_COUNT); launch_count_lines(ws, s); }
+    CK(cudaMemcpyAsync(sl.h_probe, sl.probe.p, sizeof(BlockProbe) * n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
 
     u64 lines = 0, recs = 0, syms = 0, ftab = 0, streams = 0;
     for (u32 i = 0; i < n; ++i) {
         BlockDesc& d = hd[i];
-        const u32 nl = ctx->h_probe[i].n_lines;
+        const u32 nl = sl.h_probe[i].n_lines;
         d.line_base = (u32)lines; d.line_cap = nl; lines += nl;
         d.rec_base = (u32)recs; d.rec_cap = nl / 4 + 1; recs += d.rec_cap;
         d.sym_base = syms; d.sym_cap = d.in_len / 2 + 16; syms += align_up(d.sym_cap, 16);
-        d.n_fields = ctx->h_probe[i].n_fields;
+        d.n_fields = sl.h_probe[i].n_fields;
         d.ftab_base = ftab; ftab += (u64)d.n_fields * d.rec_cap;
         d.stream_base = streams;
         d.stream_cap[0] = 64;
@@ -244,59 +276,61 @@ static int encode_batch(dsrcgpu_ctx* ctx, const u8* d_in, const u64* in_off, con
         streams += (u64)d.stream_cap[0] + d.stream_cap[1] + d.stream_cap[2] + d.stream_cap[3];
         if (lines >= (1ull << 32) || recs >= (1ull << 32)) { ctx->err = "batch too large"; return DSRCGPU_E_ARG; }
     }
-    CK(ctx->lines.ensure(lines * 4));
-    CK(ctx->r_title_off.ensure(recs * 4)); CK(ctx->r_seq_off.ensure(recs * 4)); CK(ctx->r_qua_off.ensure(recs * 4));
-    CK(ctx->r_qcat_off.ensure(recs * 4)); CK(ctx->r_dcat_off.ensure(recs * 4));
-    CK(ctx->r_title_len.ensure(recs * 2)); CK(ctx->r_qua_len.ensure(recs * 2)); CK(ctx->r_dna_len.ensure(recs * 2)); CK(ctx->r_trunc_len.ensure(recs * 2));
-    CK(ctx->qcat.ensure(syms)); CK(ctx->dcat.ensure(syms));
+    CK(sl.lines.ensure(lines * 4));
+    CK(sl.r_title_off.ensure(recs * 4)); CK(sl.r_seq_off.ensure(recs * 4)); CK(sl.r_qua_off.ensure(recs * 4));
+    CK(sl.r_qcat_off.ensure(recs * 4)); CK(sl.r_dcat_off.ensure(recs * 4));
+    CK(sl.r_title_len.ensure(recs * 2)); CK(sl.r_qua_len.ensure(recs * 2)); CK(sl.r_dna_len.ensure(recs * 2)); CK(sl.r_trunc_len.ensure(recs * 2));
+    CK(sl.qcat.ensure(syms)); CK(sl.dcat.ensure(syms));
     const bool rc_q = ctx->cs.quality_order > 0, rc_d = ctx->cs.dna_order > 0;
-    if (rc_q) CK(ctx->trip_q.ensure(syms * 8));
-    if (rc_d) CK(ctx->trip_d.ensure(syms * 8));
-    CK(ctx->ftab.ensure(ftab * 8));
-    CK(ctx->streams.ensure(streams));
-    if (rc_q || rc_d) { CK(ctx->elem_a.ensure(ctx->model_stride * 8 * ctx->model_ctas)); CK(ctx->elem_b.ensure(ctx->model_stride * 8 * ctx->model_ctas)); }
-    if ((rc_q || rc_d) && !ctx->tab.p && ctx->tab_stride) {
-        CK(ctx->tab.ensure(ctx->tab_stride * ctx->model_ctas));
-        CK(cudaMemsetAsync(ctx->tab.p, 0, ctx->tab.cap, s));      // invariant between blocks: first counter of every row is 0
+    if (rc_q) CK(sl.trip_q.ensure(syms * 8));
+    if (rc_d) CK(sl.trip_d.ensure(syms * 8));
+    CK(sl.ftab.ensure(ftab * 8));
+    CK(sl.streams.ensure(streams));
+    if (rc_q || rc_d) { CK(sl.elem_a.ensure(ctx->model_stride * 8 * ctx->model_ctas)); CK(sl.elem_b.ensure(ctx->model_stride * 8 * ctx->model_ctas)); }
+    if ((rc_q || rc_d) && !sl.tab.p && ctx->tab_stride) {
+        CK(sl.tab.ensure(ctx->tab_stride * ctx->model_ctas));
+        CK(cudaMemsetAsync(sl.tab.p, 0, sl.tab.cap, s));      // invariant between blocks: first counter of every row is 0
     }
-    CK(ctx->tagpool.ensure(tagpool_bytes_per_block() * ctx->tag_ctas));
-    if (!rc_q || !rc_d) CK(ctx->q0_arena.ensure(ctx->q0_stride * ctx->q0_ctas));
+    CK(sl.tagpool.ensure(tagpool_bytes_per_block() * ctx->tag_ctas));
+    if (!rc_q || !rc_d) CK(sl.q0_arena.ensure(ctx->q0_stride * ctx->q0_ctas));
 
-    ws.lines = (u32*)ctx->lines.p;
-    ws.rec.title_off = (u32*)ctx->r_title_off.p; ws.rec.seq_off = (u32*)ctx->r_seq_off.p; ws.rec.qua_off = (u32*)ctx->r_qua_off.p;
-    ws.rec.title_len = (u16*)ctx->r_title_len.p; ws.rec.qua_len = (u16*)ctx->r_qua_len.p; ws.rec.dna_len = (u16*)ctx->r_dna_len.p;
-    ws.rec.trunc_len = (u16*)ctx->r_trunc_len.p; ws.rec.qcat_off = (u32*)ctx->r_qcat_off.p; ws.rec.dcat_off = (u32*)ctx->r_dcat_off.p;
-    ws.qcat = (u8*)ctx->qcat.p; ws.dcat = (u8*)ctx->dcat.p;
-    ws.trip_q = (u64*)ctx->trip_q.p; ws.trip_d = (u64*)ctx->trip_d.p;
-    ws.elem_a = (u64*)ctx->elem_a.p; ws.elem_b = (u64*)ctx->elem_b.p;
-    ws.ftab = (u64*)ctx->ftab.p; ws.streams = (u8*)ctx->streams.p;
-    ws.tab = (u8*)ctx->tab.p; ws.tab_stride = ctx->tab_stride;
-    ws.tagpool = (u8*)ctx->tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
+    ws.lines = (u32*)sl.lines.p;
+    ws.rec.title_off = (u32*)sl.r_title_off.p; ws.rec.seq_off = (u32*)sl.r_seq_off.p; ws.rec.qua_off = (u32*)sl.r_qua_off.p;
+    ws.rec.title_len = (u16*)sl.r_title_len.p; ws.rec.qua_len = (u16*)sl.r_qua_len.p; ws.rec.dna_len = (u16*)sl.r_dna_len.p;
+    ws.rec.trunc_len = (u16*)sl.r_trunc_len.p; ws.rec.qcat_off = (u32*)sl.r_qcat_off.p; ws.rec.dcat_off = (u32*)sl.r_dcat_off.p;
+    ws.qcat = (u8*)sl.qcat.p; ws.dcat = (u8*)sl.dcat.p;
+    ws.trip_q = (u64*)sl.trip_q.p; ws.trip_d = (u64*)sl.trip_d.p;
+    ws.elem_a = (u64*)sl.elem_a.p; ws.elem_b = (u64*)sl.elem_b.p;
+    ws.ftab = (u64*)sl.ftab.p; ws.streams = (u8*)sl.streams.p;
+    ws.tab = (u8*)sl.tab.p; ws.tab_stride = ctx->tab_stride;
+    ws.tagpool = (u8*)sl.tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
 
-    CK(cudaMemcpyAsync(ctx->desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
-    { KTimer t(ctx, K_PARSE); launch_parse(ws, s); }
-    { KTimer t(ctx, K_PREP); launch_preprocess(ws, s); }
-    { KTimer t(ctx, K_TAGS); launch_tags(ws, s, ctx->tag_ctas); }
-    if (rc_q) { KTimer t(ctx, K_MODEL_Q); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
-    else { KTimer t(ctx, K_Q0); launch_q0_quality(ws, s, (u8*)ctx->q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
-    if (rc_d) { KTimer t(ctx, K_MODEL_D); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
-    else { KTimer t(ctx, K_D0); launch_d0_dna(ws, s, (u8*)ctx->q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
-    if (rc_q || rc_d) { KTimer t(ctx, K_RC); launch_rc_encode(ws, s); }
-    { KTimer t(ctx, K_SIZES); launch_meta_and_sizes(ws, s, out_base); }
-    { KTimer t(ctx, K_GATHER); launch_gather(ws, s); }
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    { KTimer t(ctx, &sl, K_PARSE); launch_parse(ws, s); }
+    { KTimer t(ctx, &sl, K_PREP); launch_preprocess(ws, s); }
+    { KTimer t(ctx, &sl, K_TAGS); launch_tags(ws, s, ctx->tag_ctas); }
+    if (rc_q) { KTimer t(ctx, &sl, K_MODEL_Q); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
+    else { KTimer t(ctx, &sl, K_Q0); launch_q0_quality(ws, s, (u8*)sl.q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
+    if (rc_d) { KTimer t(ctx, &sl, K_MODEL_D); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
+    else { KTimer t(ctx, &sl, K_D0); launch_d0_dna(ws, s, (u8*)sl.q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
+    if (rc_q || rc_d) { KTimer t(ctx, &sl, K_RC); launch_rc_encode(ws, s); }
+    if (wait_sizes) CK(cudaStreamWaitEvent(s, wait_sizes, 0));       // the previous batch has to publish where its output ends
+    { KTimer t(ctx, &sl, K_SIZES); launch_meta_and_sizes(ws, s, out_base, cursor); }
+    CK(cudaEventRecord(sl.ev_sizes, s));
+    { KTimer t(ctx, &sl, K_GATHER); launch_gather(ws, s); }
+    CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(sl.ev_results, s));
     CK(cudaGetLastError());
-    collect_times(ctx);
-    u64 end = out_base;
-    for (u32 i = 0; i < n; ++i) {
-        if (ctx->h_result[i].status != ST_OK) return status_to_error(ctx, ctx->h_result[i].status, i);
-        end = ctx->h_result[i].out_off + ctx->h_result[i].total_size;
-    }
-    *out_end = end;
     return DSRCGPU_OK;
 }
 
+static void abort_all(dsrcgpu_ctx* ctx)
+{
+    for (int i = 0; i < ctx->n_slots; ++i) { cudaStreamSynchronize(ctx->slots[i].stream); collect_times(ctx, &ctx->slots[i]); ctx->slots[i].busy = false; }
+}
+
+// The CUDA-stream block scheduler (replaces the worker pool + queues of DsrcCompressorMT, src/DsrcOperator.cpp:230-394):
+// the block queue is cut into batches, batch b runs on slot b % n_slots, results are retired strictly in block order.
 static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const u64* blk_off, const u32* blk_len, const u32* blk_tagcap, u32 n,
                        u8* out, u64 out_cap, u32* out_sizes, u64* raw_sizes, u64* comp_sizes)
 {
@@ -305,17 +339,56 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return DSRCGPU_E_CUDA; }
     memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
     if (!ctx->call_a) { cudaEventCreate(&ctx->call_a); cudaEventCreate(&ctx->call_b); }
-    cudaEventRecord(ctx->call_a, ctx->stream);
+    const int S = ctx->n_slots;
+    cudaEventRecord(ctx->call_a, ctx->slots[0].stream);
+    if (on_device) {
+        CK(ctx->cursor.ensure(8));
+        CK(cudaMemsetAsync(ctx->cursor.p, 0, 8, ctx->slots[0].stream));
+    }
+    const u32 nb = (n + ctx->max_inflight - 1) / ctx->max_inflight;
     u64 out_pos = 0;
-    std::vector<u64> offs;
-    for (u32 first = 0; first < n;) {
-        u32 cnt = std::min(ctx->max_inflight, n - first);
-        const u8* d_in; u8* d_out; u64 batch_out_base, batch_out_cap;
-        offs.resize(cnt);
+    u32 retired = 0;
+    int rc = DSRCGPU_OK;
+
+    auto retire = [&](u32 r) -> int {
+        Slot& t = ctx->slots[r % S];
+        CK(cudaEventSynchronize(t.ev_results));
+        collect_times(ctx, &t);
+        u64 end = on_device ? out_pos : 0;
+        for (u32 i = 0; i < t.cnt; ++i) {
+            const BlockResult& br = t.h_result[i];
+            if (br.status != ST_OK) return status_to_error(ctx, br.status, t.first + i);
+            end = br.out_off + br.total_size;
+            out_sizes[t.first + i] = br.total_size;
+            if (raw_sizes) for (int k = 0; k < 4; ++k) raw_sizes[(u64)(t.first + i) * 4 + k] = br.raw[k];
+            if (comp_sizes) for (int k = 0; k < 4; ++k) comp_sizes[(u64)(t.first + i) * 4 + k] = br.stream_size[k];
+        }
+        if (on_device) out_pos = end;
+        else {
+            if (out_pos + end > out_cap) { ctx->err = "output buffer too small"; return DSRCGPU_E_CAPACITY; }
+            CK(cudaMemcpyAsync(out + out_pos, t.out.p, end, cudaMemcpyDeviceToHost, t.stream));
+            out_pos += end;
+        }
+        return DSRCGPU_OK;
+    };
+
+    for (u32 b = 0; b < nb && rc == DSRCGPU_OK; ++b) {
+        Slot& sl = ctx->slots[b % S];
+        if (sl.busy) {
+            while (rc == DSRCGPU_OK && retired <= sl.batch) rc = retire(retired++);
+            if (rc) break;
+            cudaError_t e = cudaStreamSynchronize(sl.stream);            // its output copy has left the staging buffer
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = DSRCGPU_E_CUDA; break; }
+            sl.busy = false;
+        }
+        const u32 first = b * ctx->max_inflight, cnt = std::min(ctx->max_inflight, n - first);
+        sl.first = first; sl.cnt = cnt; sl.batch = b;
+        sl.offs.resize(cnt);
+        const u8* d_in; u8* d_out; u64 batch_out_base = 0, batch_out_cap;
         if (on_device) {
             d_in = fastq;
-            for (u32 i = 0; i < cnt; ++i) offs[i] = blk_off[first + i];
-            d_out = out; batch_out_base = out_pos; batch_out_cap = out_cap;
+            for (u32 i = 0; i < cnt; ++i) sl.offs[i] = blk_off[first + i];
+            d_out = out; batch_out_cap = out_cap;
         } else {
             // stage the batch: one copy when the blocks are a (near-)contiguous ascending span, packed copies otherwise
             u64 lo = blk_off[first], hi = 0, sum = 0; bool asc = true;
@@ -324,44 +397,43 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
                 if (i && o < blk_off[first + i - 1] + blk_len[first + i - 1]) asc = false;
                 lo = std::min(lo, o); hi = std::max(hi, o + l); sum += l;
             }
+            cudaError_t e = cudaSuccess;
             if (asc && hi - lo <= sum + (u64)cnt * 64) {
-                CK(ctx->in.ensure(hi - lo + 16));
-                CK(cudaMemcpyAsync(ctx->in.p, fastq + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
-                for (u32 i = 0; i < cnt; ++i) offs[i] = blk_off[first + i] - lo;
+                e = sl.in.ensure(hi - lo + 16);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(sl.in.p, fastq + lo, hi - lo, cudaMemcpyHostToDevice, sl.stream);
+                for (u32 i = 0; i < cnt; ++i) sl.offs[i] = blk_off[first + i] - lo;
             } else {
-                CK(ctx->in.ensure(sum + (u64)cnt * 16 + 16));
+                e = sl.in.ensure(sum + (u64)cnt * 16 + 16);
                 u64 p = 0;
-                for (u32 i = 0; i < cnt; ++i) {
-                    CK(cudaMemcpyAsync((u8*)ctx->in.p + p, fastq + blk_off[first + i], blk_len[first + i], cudaMemcpyHostToDevice, ctx->stream));
-                    offs[i] = p; p += align_up(blk_len[first + i], 16);
+                for (u32 i = 0; i < cnt && e == cudaSuccess; ++i) {
+                    e = cudaMemcpyAsync((u8*)sl.in.p + p, fastq + blk_off[first + i], blk_len[first + i], cudaMemcpyHostToDevice, sl.stream);
+                    sl.offs[i] = p; p += align_up(blk_len[first + i], 16);
                 }
             }
-            d_in = (const u8*)ctx->in.p;
             u64 bound = 0;
             for (u32 i = 0; i < cnt; ++i) bound += (u64)blk_len[first + i] + (blk_len[first + i] >> 1) + 4096;   // generous: DSRC never expands by 1.5x
-            bound = std::min(bound, out_cap - out_pos + 1);
-            CK(ctx->out.ensure(bound));
-            d_out = (u8*)ctx->out.p; batch_out_base = 0; batch_out_cap = std::min<u64>(bound, out_cap - out_pos);
+            if (e == cudaSuccess) e = sl.out.ensure(bound);
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = DSRCGPU_E_CUDA; break; }
+            d_in = (const u8*)sl.in.p;
+            d_out = (u8*)sl.out.p; batch_out_cap = bound;
         }
-        u64 end = 0;
-        int rc = encode_batch(ctx, d_in, offs.data(), blk_len + first, blk_tagcap ? blk_tagcap + first : nullptr, cnt,
-                              d_out, batch_out_base, batch_out_cap, &end);
-        if (rc) return rc;
-        for (u32 i = 0; i < cnt; ++i) {
-            const BlockResult& r = ctx->h_result[i];
-            out_sizes[first + i] = r.total_size;
-            if (raw_sizes) for (int k = 0; k < 4; ++k) raw_sizes[(u64)(first + i) * 4 + k] = r.raw[k];
-            if (comp_sizes) for (int k = 0; k < 4; ++k) comp_sizes[(u64)(first + i) * 4 + k] = r.stream_size[k];
-        }
-        if (on_device) out_pos = end;
-        else {
-            CK(cudaMemcpyAsync(out + out_pos, d_out, end, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            out_pos += end;
-        }
-        first += cnt;
+        sl.busy = true;
+        rc = enqueue_batch(ctx, sl, d_in, blk_len + first, blk_tagcap ? blk_tagcap + first : nullptr, cnt, d_out, batch_out_base, batch_out_cap,
+                           on_device ? (u64*)ctx->cursor.p : nullptr, (on_device && b > 0) ? ctx->slots[(b - 1) % S].ev_sizes : nullptr);
+        if (rc) break;
+        // keep S-1 batches queued behind the one the host waits for
+        while (rc == DSRCGPU_OK && retired + (u32)(S - 1) <= b && S > 1 && retired < b) rc = retire(retired++);
     }
-    cudaEventRecord(ctx->call_b, ctx->stream);
+    while (rc == DSRCGPU_OK && retired < nb) rc = retire(retired++);
+    if (rc) { abort_all(ctx); return rc; }
+    // join every stream into slot 0's for the call timing, then wait
+    for (int i = 1; i < S; ++i) {
+        cudaEvent_t e = get_event(ctx);
+        cudaEventRecord(e, ctx->slots[i].stream); cudaStreamWaitEvent(ctx->slots[0].stream, e, 0);
+        ctx->ev_pool.push_back(e);
+    }
+    cudaEventRecord(ctx->call_b, ctx->slots[0].stream);
+    for (int i = 0; i < S; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].stream)); ctx->slots[i].busy = false; }
     CK(cudaEventSynchronize(ctx->call_b));
     cudaEventElapsedTime(&ctx->call_ms, ctx->call_a, ctx->call_b);
     return DSRCGPU_OK;
@@ -434,12 +506,12 @@ extern "C" int dsrcgpu_device_free(dsrcgpu_ctx* ctx, void* p) { cudaSetDevice(ct
 extern "C" int dsrcgpu_memcpy_h2d(dsrcgpu_ctx* ctx, void* d, const void* h, uint64_t bytes)
 {
     cudaSetDevice(ctx->device);
-    CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return DSRCGPU_OK;
+    CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->slots[0].stream)); CK(cudaStreamSynchronize(ctx->slots[0].stream)); return DSRCGPU_OK;
 }
 extern "C" int dsrcgpu_memcpy_d2h(dsrcgpu_ctx* ctx, void* h, const void* d, uint64_t bytes)
 {
     cudaSetDevice(ctx->device);
-    CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return DSRCGPU_OK;
+    CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->slots[0].stream)); CK(cudaStreamSynchronize(ctx->slots[0].stream)); return DSRCGPU_OK;
 }
 extern "C" int dsrcgpu_host_alloc(uint64_t bytes, void** p) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? DSRCGPU_OK : DSRCGPU_E_NOMEM; }
 extern "C" int dsrcgpu_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? DSRCGPU_OK : DSRCGPU_E_CUDA; }

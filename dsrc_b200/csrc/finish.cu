@@ -5,11 +5,11 @@
 #include "kernels.h"
 
 // one CTA: meta streams + per-block totals + exclusive scan of the totals -> out_off
-__global__ void __launch_bounds__(DSRC_CTA) k_meta_sizes(Workspace ws, u64 out_base)
+__global__ void __launch_bounds__(DSRC_CTA) k_meta_sizes(Workspace ws, u64 out_base, unsigned long long* cursor)
 {
     __shared__ u32 sm[DSRC_WARPS + 1];
     __shared__ unsigned long long s_carry;
-    if (threadIdx.x == 0) s_carry = out_base;
+    if (threadIdx.x == 0) s_carry = cursor ? *cursor : out_base;      // cursor: running end of the dense output across batches (device-resident output)
     __syncthreads();
     for (u32 base = 0; base < ws.n_blocks; base += DSRC_CTA) {
         const u32 blk = base + threadIdx.x;
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(DSRC_CTA) k_meta_sizes(Workspace ws, u64 out_b
         if (threadIdx.x == 0) s_carry = carry + tile_total;
         __syncthreads();
     }
+    if (cursor && threadIdx.x == 0) *cursor = s_carry;
 }
 
 __global__ void __launch_bounds__(DSRC_CTA) k_gather(Workspace ws)
@@ -70,5 +71,5 @@ __global__ void __launch_bounds__(DSRC_CTA) k_gather(Workspace ws)
     }
 }
 
-void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base) { k_meta_sizes<<<1, DSRC_CTA, 0, s>>>(ws, out_base); }
+void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base, u64* cursor) { k_meta_sizes<<<1, DSRC_CTA, 0, s>>>(ws, out_base, (unsigned long long*)cursor); }
 void launch_gather(const Workspace& ws, cudaStream_t s) { k_gather<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }

@@ -14,7 +14,7 @@ void launch_rc_encode(const Workspace& ws, cudaStream_t s);       // serial rang
 void launch_q0_quality(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u32 ctas);
 void launch_d0_dna(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u32 ctas);
 u64 q0_arena_bytes(u64 max_block_bytes);
-void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base);  // StoreMetaData + dense output offsets (first block at out_base)
+void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base, u64* cursor);  // StoreMetaData + dense output offsets (first block at out_base, or at *cursor which is then advanced)
 void launch_gather(const Workspace& ws, cudaStream_t s);          // meta|tags|quality|dna -> dense output
 
 u64 tagpool_bytes_per_block();

@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
 // (src/RangeCoder.h:51-84); stream prologues: scheme byte (DnaModelerProxy.h:50-60, QualityModelerProxy.h:48-58)
 // and, for quality, the 256-bit symbol mask of TTranslationalQualityEncoder::Store (QualityEncoder.h:332-342).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rc_encode(Workspace ws, u32 do_quality, u32 do_dna)
+#define RC_CTA 64
+__global__ void __launch_bounds__(RC_CTA) k_rc_encode(Workspace ws, u32 do_quality, u32 do_dna)
 {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 n = ws.n_blocks;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(128) k_rc_encode(Workspace ws, u32 do_quality,
     BlockState& st = ws.state[blk];
     if (st.status != ST_OK) return;
     const int sidx = is_dna ? 2 : 3;
-    u8* out = ws.streams + d.stream_base + stream_offset(d, sidx);
+    u8* out = ws.streams + d.stream_base + stream_offset(d, sidx);       // 16-byte aligned
     const u32 cap = d.stream_cap[sidx];
     const u32 scheme = is_dna ? st.d_scheme : st.q_scheme;
     u32 pos = 0;
@@ -459,25 +460,47 @@ __global__ void __launch_bounds__(128) k_rc_encode(Workspace ws, u32 do_quality,
         }
     }
     const u32 M = is_dna ? st.d_total : st.q_total;
-    if ((u64)pos + 3ull * M + 16 > cap) { st.status = ST_OVERFLOW; return; }
-    const u64* trip = (is_dna ? ws.trip_d : ws.trip_q) + d.sym_base;
+    if ((u64)pos + 3ull * M + 24 > cap) { st.status = ST_OVERFLOW; return; }
+    // the chain's triples arrive 4 at a time (one 32-byte sector per load, two sectors in flight); its output bytes leave 8 at a time
+    const ulonglong2* trip = (const ulonglong2*)((is_dna ? ws.trip_d : ws.trip_q) + d.sym_base);
+    const u32 G = (M + 3) / 4;                         // groups of 4 triples; the arena has >= 16 entries of slack behind M
     u64 low = 0; u32 range = 0xFFFFFFFFu;
-    u64 nxt = M ? trip[0] : 0;
-    for (u32 i = 0; i < M; ++i) {
-        const u64 tr = nxt;
-        if (i + 1 < M) nxt = trip[i + 1];
-        const u32 f = (u32)tr & 0xFFFFu, cum = (u32)(tr >> 16) & 0xFFFFu, tot = (u32)(tr >> 32);
-        range /= tot;
-        low += (u64)(range * cum);
-        range *= f;
-        while (range <= 0x00FFFFFFu) {
-            if ((low ^ (low + range)) & 0xFF00000000000000ull) { u32 r = (u32)low; range = (r | 0x00FFFFFFu) - r; }
-            out[pos++] = (u8)(low >> 56);
-            low <<= 8; range <<= 8;
-        }
+    u64 obuf = 0; u32 on = pos & 7u;
+    pos &= ~7u;
+    for (u32 k = 0; k < on; ++k) obuf |= (u64)out[pos + k] << (8 * k);
+#define RC_PUT(b) do { obuf |= (u64)(u8)(b) << (8 * on); if (++on == 8) { *(u64*)(out + pos) = obuf; pos += 8; obuf = 0; on = 0; } } while (0)
+#define RC_STEP(tr) do { \
+        const u32 f_ = (u32)(tr) & 0xFFFFu, cum_ = (u32)((tr) >> 16) & 0xFFFFu, tot_ = (u32)((tr) >> 32); \
+        range /= tot_; low += (u64)(range * cum_); range *= f_; \
+        while (range <= 0x00FFFFFFu) { \
+            if ((low ^ (low + range)) & 0xFF00000000000000ull) { const u32 r_ = (u32)low; range = (r_ | 0x00FFFFFFu) - r_; } \
+            RC_PUT(low >> 56); low <<= 8; range <<= 8; \
+        } } while (0)
+    ulonglong2 a0, a1, b0, b1;
+    a0 = a1 = b0 = b1 = make_ulonglong2(0, 0);
+    if (G > 0) { a0 = __ldcs(trip + 0); a1 = __ldcs(trip + 1); }
+    if (G > 1) { b0 = __ldcs(trip + 2); b1 = __ldcs(trip + 3); }
+    u32 i = 0;
+    for (u32 g = 0; g < G; g += 2) {
+        const ulonglong2 c0 = a0, c1 = a1;
+        if (g + 2 < G) { a0 = __ldcs(trip + 2 * (g + 2)); a1 = __ldcs(trip + 2 * (g + 2) + 1); }
+        if (i < M) { RC_STEP(c0.x); ++i; }
+        if (i < M) { RC_STEP(c0.y); ++i; }
+        if (i < M) { RC_STEP(c1.x); ++i; }
+        if (i < M) { RC_STEP(c1.y); ++i; }
+        if (g + 1 >= G) break;
+        const ulonglong2 e0 = b0, e1 = b1;
+        if (g + 3 < G) { b0 = __ldcs(trip + 2 * (g + 3)); b1 = __ldcs(trip + 2 * (g + 3) + 1); }
+        if (i < M) { RC_STEP(e0.x); ++i; }
+        if (i < M) { RC_STEP(e0.y); ++i; }
+        if (i < M) { RC_STEP(e1.x); ++i; }
+        if (i < M) { RC_STEP(e1.y); ++i; }
     }
-    for (int k = 0; k < 8; ++k) { out[pos++] = (u8)(low >> 56); low <<= 8; }
-    st.stream_size[sidx] = pos;
+    for (int k = 0; k < 8; ++k) { RC_PUT(low >> 56); low <<= 8; }
+    for (u32 k = 0; k < on; ++k) out[pos + k] = (u8)(obuf >> (8 * k));
+    st.stream_size[sidx] = pos + on;
+#undef RC_STEP
+#undef RC_PUT
 }
 
 static u32 model_grid(const Workspace& ws, u32 max_ctas)
@@ -493,5 +516,5 @@ void launch_rc_encode(const Workspace& ws, cudaStream_t s)
     const u32 dq = ws.qua_order > 0, dd = ws.dna_order > 0;
     if (!dq && !dd) return;
     const u32 threads = ws.n_blocks * (dq + dd);
-    k_rc_encode<<<(threads + 127) / 128, 128, 0, s>>>(ws, dq, dd);
+    k_rc_encode<<<(threads + RC_CTA - 1) / RC_CTA, RC_CTA, 0, s>>>(ws, dq, dd);
 }

@@ -13,7 +13,7 @@ import torch  # noqa: E402
 
 reads = int(sys.argv[1]) if len(sys.argv) > 1 else 5_000_000
 profile = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-inflight = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+inflight = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
 d_order = int(sys.argv[4]) if len(sys.argv) > 4 else 6
 q_order = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 L = _lib.lib()
