@@ -439,6 +439,174 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     return DSRCGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// decode: BlockCompressor::Read for a queue of blocks
+// ------------------------------------------------------------------------------------------------
+#define DEC_POOL_NODES 32768u            // Huffman nodes (8 B) per block
+#define DEC_ST_RETRY 4u
+
+// one (sub-)batch: blocks `idx[0..n)` of the call, already staged at offs[] in d_in; out_offs[] are absolute offsets in d_out
+static int decode_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* idx, const u64* offs, const u32* blk_len, const u64* out_offs,
+                        u32 n, u8* d_out, u64 out_cap, u64 arena_bytes, u32* status_out, u32* size_out)
+{
+    int rc = ensure_host(ctx, sl, n);
+    if (rc) return rc;
+    cudaStream_t s = sl.stream;
+    CK(sl.desc.ensure(sizeof(BlockDesc) * n)); CK(sl.state.ensure(sizeof(BlockState) * n));
+    CK(sl.result.ensure(sizeof(BlockResult) * n)); CK(sl.probe.ensure(sizeof(BlockProbe) * n));
+    BlockDesc* hd = sl.h_desc;
+    for (u32 i = 0; i < n; ++i) { memset(&hd[i], 0, sizeof(BlockDesc)); hd[i].in_off = offs[i]; hd[i].in_len = blk_len[idx[i]]; }
+    Workspace ws{};
+    ws.in = d_in; ws.desc = (const BlockDesc*)sl.desc.p; ws.state = (BlockState*)sl.state.p;
+    ws.result = (BlockResult*)sl.result.p; ws.probe = (BlockProbe*)sl.probe.p;
+    ws.n_blocks = n; ws.qoff = ctx->ds.quality_offset; ws.plus_rep = ctx->ds.plus_repetition;
+    ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order;
+    ws.out = d_out; ws.out_cap = out_cap;
+    CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    { KTimer t(ctx, &sl, K_DECODE); launch_dec_probe(ws, s); }
+    CK(cudaMemcpyAsync(sl.h_probe, sl.probe.p, sizeof(BlockProbe) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    u64 recs = 0, syms = 0, titles = 0;
+    for (u32 i = 0; i < n; ++i) {
+        BlockDesc& d = hd[i];
+        const u32 nr = sl.h_probe[i].n_lines, chunk = sl.h_probe[i].n_fields;      // records, chunkSize + 1
+        d.rec_base = (u32)recs; d.rec_cap = nr; recs += nr;
+        d.sym_base = syms; d.sym_cap = chunk / 2 + 16; syms += align_up(d.sym_cap, 16);
+        d.stream_base = titles; d.stream_cap[1] = (u32)align_up((u64)chunk + 16, 16); titles += d.stream_cap[1];
+        d.out_off = out_offs[i];
+        if (chunk && out_offs[i] + chunk > out_cap) { ctx->err = "output buffer too small"; return DSRCGPU_E_CAPACITY; }
+        if (recs >= (1ull << 32)) { ctx->err = "batch too large"; return DSRCGPU_E_ARG; }
+    }
+    CK(sl.r_title_off.ensure(recs * 4 + 16)); CK(sl.r_seq_off.ensure(recs * 4 + 16)); CK(sl.r_qcat_off.ensure(recs * 4 + 16)); CK(sl.r_dcat_off.ensure(recs * 4 + 16));
+    CK(sl.r_title_len.ensure(recs * 2 + 16)); CK(sl.r_qua_len.ensure(recs * 2 + 16)); CK(sl.r_dna_len.ensure(recs * 2 + 16));
+    CK(sl.qcat.ensure(syms)); CK(sl.dcat.ensure(syms)); CK(sl.streams.ensure(titles + 16));
+    CK(sl.ftab.ensure((u64)DEC_POOL_NODES * 8 * n));
+    const bool rcq = ctx->cs.quality_order > 0, rcd = ctx->cs.dna_order > 0;
+    if (rcq || rcd) CK(ctx->dec_arena.ensure(arena_bytes * n));
+    ws.rec.title_off = (u32*)sl.r_title_off.p; ws.rec.seq_off = (u32*)sl.r_seq_off.p; ws.rec.qcat_off = (u32*)sl.r_qcat_off.p; ws.rec.dcat_off = (u32*)sl.r_dcat_off.p;
+    ws.rec.title_len = (u16*)sl.r_title_len.p; ws.rec.qua_len = (u16*)sl.r_qua_len.p; ws.rec.dna_len = (u16*)sl.r_dna_len.p;
+    ws.qcat = (u8*)sl.qcat.p; ws.dcat = (u8*)sl.dcat.p; ws.streams = (u8*)sl.streams.p;
+    CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    { KTimer t(ctx, &sl, K_DECODE); launch_dec_tags(ws, s, sl.ftab.p, DEC_POOL_NODES); }
+    if (rcq) CK(cudaMemsetAsync(ctx->dec_arena.p, 0, arena_bytes * n, s));
+    { KTimer t(ctx, &sl, K_DECODE); launch_dec_quality(ws, s, sl.ftab.p, DEC_POOL_NODES, (u8*)ctx->dec_arena.p, arena_bytes, arena_bytes); }
+    if (rcd) CK(cudaMemsetAsync(ctx->dec_arena.p, 0, arena_bytes * n, s));
+    { KTimer t(ctx, &sl, K_DECODE); launch_dec_dna(ws, s, sl.ftab.p, DEC_POOL_NODES, (u8*)ctx->dec_arena.p, arena_bytes, arena_bytes); }
+    { KTimer t(ctx, &sl, K_DECODE); launch_dec_assemble(ws, s); }
+    CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    collect_times(ctx, &sl);
+    for (u32 i = 0; i < n; ++i) { status_out[i] = sl.h_result[i].status; size_out[i] = sl.h_probe[i].n_fields; }
+    return DSRCGPU_OK;
+}
+
+static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u64* blk_off, const u32* blk_len, u32 n,
+                       u8* out, u64 out_cap, u64* out_sizes)
+{
+    if (!ctx) return DSRCGPU_E_ARG;
+    if (!dsrc || !blk_off || !blk_len || !out || !out_sizes) { ctx->err = "null argument"; return DSRCGPU_E_ARG; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return DSRCGPU_E_CUDA; }
+    memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
+    if (!ctx->call_a) { cudaEventCreate(&ctx->call_a); cudaEventCreate(&ctx->call_b); }
+    Slot& sl = ctx->slots[0];
+    cudaEventRecord(ctx->call_a, sl.stream);
+    // full-size tables of the chain rows for this configuration (second-chance decode of blocks whose hash filled up)
+    u64 big = 4ull << 20;
+    if (ctx->cs.quality_order == 2) big = 64ull << 20;
+    if (ctx->cs.dna_order) { const u32 o = ctx->cs.dna_order, o8 = o > 7 ? 7 : o; big = std::max<u64>(big, std::max<u64>((1ull << (2 * o)) * 8, (1ull << (3 * o8)) * 16)); }
+    const u64 small = 4ull << 20, budget = 16ull << 30;
+    const u32 per_batch = (u32)std::max<u64>(1, std::min<u64>(ctx->max_inflight, budget / small));
+    std::vector<u32> idx, status, sizes, retry; std::vector<u64> offs, ooffs;
+    u64 out_pos = 0;
+    for (u32 first = 0; first < n; first += per_batch) {
+        const u32 cnt = std::min(per_batch, n - first);
+        idx.resize(cnt); offs.resize(cnt); ooffs.resize(cnt); status.resize(cnt); sizes.resize(cnt);
+        for (u32 i = 0; i < cnt; ++i) idx[i] = first + i;
+        const u8* d_in; u8* d_out; u64 cap;
+        if (on_device) { d_in = dsrc; for (u32 i = 0; i < cnt; ++i) offs[i] = blk_off[first + i]; d_out = out; cap = out_cap; }
+        else {
+            u64 p = 0;
+            for (u32 i = 0; i < cnt; ++i) p += align_up(blk_len[first + i], 16);
+            CK(sl.in.ensure(p + 16));
+            p = 0;
+            // compressed blocks of a batch are normally adjacent in the archive: coalesce adjacent ones into one copy
+            for (u32 i = 0; i < cnt;) {
+                u32 j = i; u64 span = blk_len[first + i];
+                while (j + 1 < cnt && blk_off[first + j + 1] == blk_off[first + j] + blk_len[first + j]) { ++j; span += blk_len[first + j]; }
+                CK(cudaMemcpyAsync((u8*)sl.in.p + p, dsrc + blk_off[first + i], span, cudaMemcpyHostToDevice, sl.stream));
+                u64 q = p;
+                for (u32 k = i; k <= j; ++k) { offs[k] = q; q += blk_len[first + k]; }
+                p = align_up(q, 16); i = j + 1;
+            }
+            d_in = (const u8*)sl.in.p; d_out = nullptr; cap = 0;
+        }
+        // sizes first: every block stores chunkSize (BlockCompressor.cpp:302-308) -- probe pass inside decode_batch gives them, but the
+        // output offsets are needed before; read the 4 bytes at offset 12 of each block on the host when the input is host memory
+        u64 batch_bytes = 0;
+        if (!on_device) {
+            for (u32 i = 0; i < cnt; ++i) {
+                const u8* b = dsrc + blk_off[first + i];
+                const u32 chunk = blk_len[first + i] >= 16 ? (((u32)b[12] << 24) | ((u32)b[13] << 16) | ((u32)b[14] << 8) | b[15]) : 0;
+                ooffs[i] = batch_bytes; batch_bytes += (u64)chunk + 1;
+            }
+            CK(sl.out.ensure(batch_bytes + 16));
+            d_out = (u8*)sl.out.p; cap = batch_bytes;
+            if (out_pos + batch_bytes > out_cap) { ctx->err = "output buffer too small"; return DSRCGPU_E_CAPACITY; }
+        } else {
+            // device-resident input: one probe launch reads every block header (ReadMetaData) for the output offsets
+            int prc = ensure_host(ctx, sl, cnt);
+            if (prc) return prc;
+            CK(sl.desc.ensure(sizeof(BlockDesc) * cnt)); CK(sl.state.ensure(sizeof(BlockState) * cnt)); CK(sl.probe.ensure(sizeof(BlockProbe) * cnt));
+            for (u32 i = 0; i < cnt; ++i) { memset(&sl.h_desc[i], 0, sizeof(BlockDesc)); sl.h_desc[i].in_off = offs[i]; sl.h_desc[i].in_len = blk_len[first + i]; }
+            Workspace pw{};
+            pw.in = d_in; pw.desc = (const BlockDesc*)sl.desc.p; pw.state = (BlockState*)sl.state.p; pw.probe = (BlockProbe*)sl.probe.p; pw.n_blocks = cnt;
+            CK(cudaMemcpyAsync(sl.desc.p, sl.h_desc, sizeof(BlockDesc) * cnt, cudaMemcpyHostToDevice, sl.stream));
+            launch_dec_probe(pw, sl.stream);
+            CK(cudaMemcpyAsync(sl.h_probe, sl.probe.p, sizeof(BlockProbe) * cnt, cudaMemcpyDeviceToHost, sl.stream));
+            CK(cudaStreamSynchronize(sl.stream));
+            for (u32 i = 0; i < cnt; ++i) { ooffs[i] = out_pos + batch_bytes; batch_bytes += sl.h_probe[i].n_fields ? sl.h_probe[i].n_fields : 1; }
+        }
+        int rc = decode_batch(ctx, sl, d_in, idx.data(), offs.data(), blk_len, ooffs.data(), cnt, d_out, cap, small, status.data(), sizes.data());
+        if (rc) return rc;
+        retry.clear();
+        for (u32 i = 0; i < cnt; ++i) {
+            if (status[i] == DEC_ST_RETRY) { retry.push_back(i); continue; }
+            if (status[i] != ST_OK) { int e = status_to_error(ctx, status[i], first + i); if (e == DSRCGPU_E_MALFORMED) ctx->err += " (corrupt compressed block)"; return e; }
+        }
+        const u32 group = (u32)std::max<u64>(1, budget / big);
+        for (size_t g0 = 0; g0 < retry.size(); g0 += group) {
+            const u32 gn = (u32)std::min<size_t>(group, retry.size() - g0);
+            std::vector<u32> gi(gn), gs(gn), gz(gn); std::vector<u64> go(gn), goo(gn);
+            for (u32 k = 0; k < gn; ++k) { const u32 i = retry[g0 + k]; gi[k] = first + i; go[k] = offs[i]; goo[k] = ooffs[i]; }
+            rc = decode_batch(ctx, sl, d_in, gi.data(), go.data(), blk_len, goo.data(), gn, d_out, cap, big, gs.data(), gz.data());
+            if (rc) return rc;
+            for (u32 k = 0; k < gn; ++k) if (gs[k] != ST_OK) return status_to_error(ctx, gs[k], gi[k]);
+        }
+        for (u32 i = 0; i < cnt; ++i) out_sizes[first + i] = sizes[i];
+        if (!on_device) {
+            CK(cudaMemcpyAsync(out + out_pos, d_out, batch_bytes, cudaMemcpyDeviceToHost, sl.stream));
+            CK(cudaStreamSynchronize(sl.stream));
+        }
+        out_pos += batch_bytes;
+    }
+    cudaEventRecord(ctx->call_b, sl.stream);
+    CK(cudaEventSynchronize(ctx->call_b));
+    cudaEventElapsedTime(&ctx->call_ms, ctx->call_a, ctx->call_b);
+    return DSRCGPU_OK;
+}
+
+extern "C" int dsrcgpu_decode_blocks(dsrcgpu_ctx* ctx, const uint8_t* dsrc, const uint64_t* blk_off, const uint32_t* blk_len,
+                                     uint32_t n, uint8_t* fastq_out, uint64_t out_cap, uint64_t* out_sizes)
+{
+    return decode_impl(ctx, dsrc, false, blk_off, blk_len, n, fastq_out, out_cap, out_sizes);
+}
+extern "C" int dsrcgpu_decode_blocks_device(dsrcgpu_ctx* ctx, const uint8_t* d_dsrc, const uint64_t* blk_off, const uint32_t* blk_len,
+                                            uint32_t n, uint8_t* d_fastq_out, uint64_t out_cap, uint64_t* out_sizes)
+{
+    return decode_impl(ctx, d_dsrc, true, blk_off, blk_len, n, d_fastq_out, out_cap, out_sizes);
+}
+
 extern "C" float dsrcgpu_last_call_ms(dsrcgpu_ctx* ctx) { return ctx ? ctx->call_ms : 0.f; }
 
 // IFastqStreamReader::ReadNextChunk + GetNextRecordPos (src/FastqStream.cpp:18-98) over an in-memory file: the block

@@ -18,3 +18,10 @@ void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base, u6
 void launch_gather(const Workspace& ws, cudaStream_t s);          // meta|tags|quality|dna -> dense output
 
 u64 tagpool_bytes_per_block();
+
+// decode (decode.cu): one thread per block for the bit-serial parts, one CTA per block for the FASTQ assembly
+void launch_dec_probe(const Workspace& ws, cudaStream_t s);
+void launch_dec_tags(const Workspace& ws, cudaStream_t s, void* pool, u32 pool_stride);
+void launch_dec_quality(const Workspace& ws, cudaStream_t s, void* pool, u32 pool_stride, u8* arena, u64 arena_stride, u64 arena_bytes);
+void launch_dec_dna(const Workspace& ws, cudaStream_t s, void* pool, u32 pool_stride, u8* arena, u64 arena_stride, u64 arena_bytes);
+void launch_dec_assemble(const Workspace& ws, cudaStream_t s);
