@@ -32,4 +32,7 @@ def small_cases():
     sk = synth.skewed(5000)
     for d, q in [(6, 2), (9, 1), (3, 2)]:
         c.append(("skewed_rescale_d%d_q%d" % (d, q), sk, d, q, 0))
+    rq = synth.random_quals(1500)
+    for d, q in [(6, 2), (9, 1)]:
+        c.append(("randq60_d%d_q%d" % (d, q), rq, d, q, 0))
     return c

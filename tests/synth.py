@@ -116,3 +116,12 @@ def skewed(n_reads, length=150, seed=8, p_major=0.97):
     lv = np.array([2, 12, 23, 37], dtype=np.uint8) + 33
     qual = np.where(rng.random((n_reads, length)) < p_major, ord("I"), lv[rng.integers(0, 4, size=(n_reads, length))]).astype(np.uint8)
     return b"".join(b"@SK.%d 1:N:0\n" % (i + 1) + seq[i].tobytes() + b"\n+\n" + qual[i].tobytes() + b"\n" for i in range(n_reads))
+
+
+def random_quals(n_reads, length=150, seed=9, n_levels=60):
+    """uniformly random qualities over many levels: tens of thousands of distinct order-2 contexts in one block
+    (exercises the 64-symbol models and, on the GPU decode path, the full-table retry of a filled context hash)."""
+    rng = np.random.default_rng(seed)
+    seq = BASES[rng.integers(0, 4, size=(n_reads, length))]
+    qual = (rng.integers(0, n_levels, size=(n_reads, length)) + 33).astype(np.uint8)
+    return b"".join(b"@RQ.%d\n" % (i + 1) + seq[i].tobytes() + b"\n+\n" + qual[i].tobytes() + b"\n" for i in range(n_reads))
