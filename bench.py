@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=4096, help="blocks per batch (one batch per stream slot)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -295,6 +296,27 @@ def main():
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
         e2e = {"value": payload * world / (float(tv[0]) / args.steps) / 1e6, "unit": "MB/s",
                "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(sizes.astype(np.uint64).sum())}
+    # decode leg (BASELINE configs[4], bounded sample): BlockCompressor::Read of the first blocks of the archive just written,
+    # device-resident, verified byte for byte against the input
+    dec = None
+    if not args.no_decode:
+        nd = min(n, 8192)
+        step_device()
+        coffs = np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))[:-1]]).astype(np.uint64)
+        dbytes = int(lens[:nd].astype(np.uint64).sum()) + nd
+        d_dec = torch.empty(dbytes + 64, dtype=torch.uint8, device="cuda")
+        osz = np.zeros(nd, dtype=np.uint64)
+
+        def step_decode():
+            check(L.dsrcgpu_decode_blocks_device(ctx, C.c_void_p(d_out.data_ptr()), coffs.ctypes.data_as(_lib.u64p), sizes.ctypes.data_as(_lib.u32p), nd,
+                                                 C.c_void_p(d_dec.data_ptr()), dbytes + 64, osz.ctypes.data_as(_lib.u64p)), "decode_device")
+            return float(L.dsrcgpu_last_call_ms(ctx))
+        step_decode()
+        dms = min(step_decode() for _ in range(2))
+        ok = bool(int(osz.sum()) == dbytes and torch.equal(d_dec[:dbytes], d_in[int(offs[0]):int(offs[0]) + dbytes]))
+        dec = {"value": dbytes / dms / 1e3, "unit": "MB/s", "blocks": int(nd), "bytes": dbytes, "verified_identical": ok,
+               "note": "device-resident decode of the first blocks of this step's archive, one stream, max over 2 runs"}
+        del d_dec
     sampler.stop = True
     sampler.join(timeout=2)
 
@@ -332,7 +354,7 @@ def main():
                 "data": "synthetic", "config": config, "clocks": sampler.summary(), "gpu_launches": launches,
                 "device_ms_per_step": dev_max * 1e3 / args.steps, "ratio": payload / max(1, comp_bytes),
                 "blocks_per_gpu": int(n), "parity_checked_blocks": parity_blocks,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "decode": dec}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

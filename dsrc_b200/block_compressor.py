@@ -62,12 +62,16 @@ class BlockCompressor:
             self.tag_capacity = self.L.dsrcgpu_tag_capacity_after(int(self.tag_capacity), nf)
         return caps
 
-    def store_many(self, data, offs, lens, warm=False):
-        """data: bytes-like holding the blocks; returns (list of compressed blocks, raw sizes [n,4], comp sizes [n,4])."""
+    def store_many(self, data, offs, lens, warm=False, caps=None):
+        """data: bytes-like holding the blocks; returns (list of compressed blocks, raw sizes [n,4], comp sizes [n,4]).
+        caps: explicit TagStats::fields capacities per block (SURVEY 8-Q1); default: this instance's running state."""
         n = len(offs)
         offs_a = np.ascontiguousarray(offs, dtype=np.uint64)
         lens_a = np.ascontiguousarray(lens, dtype=np.uint32)
-        caps = None if warm else self._tagcaps(data, offs, lens)
+        if caps is not None:
+            caps = np.ascontiguousarray(caps, dtype=np.uint32)
+        elif not warm:
+            caps = self._tagcaps(data, offs, lens)
         buf = np.frombuffer(data, dtype=np.uint8)
         cap = int(lens_a.astype(np.uint64).sum()) * 3 // 2 + 4096 * n + 65536
         out = np.empty(cap, dtype=np.uint8)

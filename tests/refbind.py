@@ -29,6 +29,8 @@ class Oracle:
         L.dsrc_oracle_compress_mem.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, _u8p, C.c_uint64]
         L.dsrc_oracle_decompress_mem.restype = C.c_int64
         L.dsrc_oracle_decompress_mem.argtypes = [C.c_char_p, C.c_uint64, _u8p, C.c_uint64]
+        L.dsrc_oracle_analyze.restype = C.c_int
+        L.dsrc_oracle_analyze.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         self.h = L.dsrc_oracle_create(qoff, plus_rep, dna_order, qua_order)
 
     def __del__(self):
@@ -54,6 +56,13 @@ class Oracle:
         if n < 0:
             raise RuntimeError("oracle read failed: %d" % n)
         return bytes(out[:n])
+
+    def analyze(self, chunk, qoff=0):
+        q = C.c_uint32(qoff)
+        pr = C.c_int(0)
+        cs = C.c_int(0)
+        ok = self.lib.dsrc_oracle_analyze(chunk, len(chunk), C.byref(q), C.byref(pr), C.byref(cs))
+        return ok, q.value, bool(pr.value), bool(cs.value)
 
     def cut(self, data, cbuf):
         n = self.lib.dsrc_oracle_cut_blocks(data, len(data), cbuf, None, None, 0)

@@ -1,0 +1,123 @@
+"""Host logic of the operator layer (no device work): first-chunk analysis, container header/footer, block sharding, and the
+two-rank path over gloo with the oracle standing in for the device encoder."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import refbind
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_encoder(data, offs, lens, caps, st):
+    """test stand-in for the device call: one oracle instance per block, its field-vector capacity forced through a warm-up title"""
+    out = []
+    for o, l, c in zip(offs, lens, caps):
+        ora = refbind.Oracle(st["quality_offset"], int(st["plus_repetition"]), st["dna_order"], st["quality_order"])
+        chunk = bytes(memoryview(data)[int(o):int(o) + int(l)])
+        if c:        # bring TagStats::fields to capacity c: a block whose first title has c fields (2 records so Analyze-free Store works)
+            title = b"@" + b" ".join([b"x"] * int(c))
+            ora.store(title + b"\nA\n+\nI\n" + title + b"\nA\n+\nI")
+        out.append(ora.store(chunk)[0])
+    return out
+
+
+def test_analyze_first_chunk_matches_oracle():
+    from dsrc_b200.operators import analyze_first_chunk
+    o = refbind.Oracle()
+    for data in [synth.illumina(50, seed=1), synth.illumina(40, seed=2, plus_rep=True), synth.ion454(30, seed=3), synth.illumina(30, seed=4, crlf=True)]:
+        chunk = data[:-1]
+        ok, q, pr, cs = o.analyze(chunk)
+        assert ok == 1
+        assert analyze_first_chunk(chunk) == (q, pr, cs)
+    # Illumina 1.3+ offset 64
+    hi = synth.illumina(30, seed=5).replace(b"\n+\n", b"\n+\n")
+    recs = hi.split(b"\n")
+    for i in range(3, len(recs), 4):
+        recs[i] = bytes(min(126, c + 31) for c in recs[i])
+    hi = b"\n".join(recs)
+    ok, q, pr, cs = o.analyze(hi[:-1])
+    assert ok == 1 and q == 64
+    assert analyze_first_chunk(hi[:-1]) == (64, pr, cs)
+
+
+def test_header_footer_match_oracle_archive():
+    from dsrc_b200 import operators as op
+    big = synth.illumina(8000, seed=7)
+    arc = refbind.Oracle().compress(big, 2, 2, 1 << 20, 0)
+    offs, sizes, st = op.read_archive_index(arc)
+    assert st == dict(quality_offset=33, plus_repetition=False, dna_order=6, quality_order=2)
+    footer = op.write_footer(sizes, 33, False, 6, 2)
+    total = int(sizes.astype(np.uint64).sum())
+    assert op.write_header(len(footer), 40 + total, len(sizes)) == arc[:40]
+    assert footer == arc[40 + total:]
+    assert int(offs[0]) == 40
+
+
+def test_shard_ranges_cover_and_balance():
+    from dsrc_b200.operators import shard_ranges
+    lens = np.array([100] * 37 + [5000] + [100] * 10, dtype=np.uint32)
+    for world in (1, 2, 3, 8, 64):
+        rs = shard_ranges(lens, world)
+        assert rs[0][0] == 0 and rs[-1][1] == len(lens)
+        assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert all(a <= b for a, b in rs)
+
+
+def test_single_rank_archive_with_standin_encoder_matches_oracle():
+    from dsrc_b200.operators import DsrcCompressorMT, InputParameters
+    big = synth.illumina(6000, seed=21, small_field=True)
+    args = InputParameters(2, 2, 1, 0, block_bytes=1 << 18)
+    arc, _ = DsrcCompressorMT(encoder=_oracle_encoder).process(args, big)
+    assert arc == refbind.Oracle().compress(big, 2, 2, 1 << 18, 0)
+
+
+def _rank_main(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from dsrc_b200.operators import DsrcCompressorMT, InputParameters
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+
+    def gather(sizes):
+        out = [None] * world
+        dist.all_gather_object(out, sizes)
+        return out
+
+    big = synth.illumina(6000, seed=21, small_field=True)
+    args = InputParameters(2, 2, 1, 0, block_bytes=1 << 18)
+    arc, (off, payload) = DsrcCompressorMT(encoder=_oracle_encoder, gather=gather, rank=rank, world=world).process(args, big)
+    q.put((rank, arc, off, payload))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_over_gloo_assemble_the_reference_archive():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+    header, footer = res[0][1]
+    assert res[1][1] is None
+    total = sum(len(r[3]) for r in res)
+    out = bytearray(40 + total + len(footer))
+    out[:40] = header
+    for _, _, off, payload in res:           # every rank pwrites its slice at 40 + exclusive scan of the gathered sizes
+        out[off:off + len(payload)] = payload
+    out[40 + total:] = footer
+    big = synth.illumina(6000, seed=21, small_field=True)
+    assert bytes(out) == refbind.Oracle().compress(big, 2, 2, 1 << 18, 0)
+    assert res[1][2] > 40 and len(res[1][3]) > 0
