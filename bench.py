@@ -300,8 +300,9 @@ def main():
     # device-resident, verified byte for byte against the input
     dec = None
     if not args.no_decode:
-        nd = min(n, 8192)
+        nd = min(n, 32768)
         step_device()
+        L.dsrcgpu_release_workspace(ctx)      # the encode slots' workspaces make room for the decode chains' arenas
         coffs = np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))[:-1]]).astype(np.uint64)
         dbytes = int(lens[:nd].astype(np.uint64).sum()) + nd
         d_dec = torch.empty(dbytes + 64, dtype=torch.uint8, device="cuda")

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdsrc_b200.so")
+LIB_PATH = os.environ.get("DSRC_B200_LIB") or os.path.join(HERE, "libdsrc_b200.so")   # override: developer A/B builds only
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -57,6 +57,8 @@ def lib():
     L.dsrcgpu_set_profiling.argtypes = [vp, C.c_int]
     L.dsrcgpu_phase_cycles.restype = C.c_int
     L.dsrcgpu_phase_cycles.argtypes = [vp, u64p, C.c_int]
+    L.dsrcgpu_release_workspace.restype = C.c_int
+    L.dsrcgpu_release_workspace.argtypes = [vp]
     L.dsrcgpu_device_alloc.restype = C.c_int
     L.dsrcgpu_device_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.dsrcgpu_device_free.restype = C.c_int

@@ -20,6 +20,7 @@ def build(force=False, verbose=False):
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
     if verbose:
         flags += ["-Xptxas", "-v"]
+    flags += os.environ.get("DSRC_NVCC_FLAGS", "").split()
     procs = []
     objs = []
     for s in srcs:

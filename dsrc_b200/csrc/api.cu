@@ -30,9 +30,9 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_NUM };
+enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_DEC_TAGS, K_DEC_Q, K_DEC_D, K_DEC_ASM, K_NUM };
 static const char* K_NAMES[K_NUM] = {"count_lines", "parse", "preprocess", "tags", "model_quality", "model_dna", "rc_encode",
-                                     "q0_quality", "d0_dna", "meta_sizes", "gather", "decode"};
+                                     "q0_quality", "d0_dna", "meta_sizes", "gather", "decode_probe", "decode_tags", "decode_quality", "decode_dna", "decode_assemble"};
 #define MAX_SLOTS 4
 
 // One in-flight batch of blocks: its own stream, workspace and pinned staging. The scheduler keeps several slots busy so
@@ -442,12 +442,11 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
 // ------------------------------------------------------------------------------------------------
 // decode: BlockCompressor::Read for a queue of blocks
 // ------------------------------------------------------------------------------------------------
-#define DEC_POOL_NODES 32768u            // Huffman nodes (8 B) per block
 #define DEC_ST_RETRY 4u
 
 // one (sub-)batch: blocks `idx[0..n)` of the call, already staged at offs[] in d_in; out_offs[] are absolute offsets in d_out
 static int decode_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* idx, const u64* offs, const u32* blk_len, const u64* out_offs,
-                        u32 n, u8* d_out, u64 out_cap, u64 arena_bytes, u32* status_out, u32* size_out)
+                        u32 n, u8* d_out, u64 out_cap, u64 arena_bytes, u32 pool_nodes, u32* status_out, u32* size_out)
 {
     int rc = ensure_host(ctx, sl, n);
     if (rc) return rc;
@@ -480,19 +479,19 @@ static int decode_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* i
     CK(sl.r_title_off.ensure(recs * 4 + 16)); CK(sl.r_seq_off.ensure(recs * 4 + 16)); CK(sl.r_qcat_off.ensure(recs * 4 + 16)); CK(sl.r_dcat_off.ensure(recs * 4 + 16));
     CK(sl.r_title_len.ensure(recs * 2 + 16)); CK(sl.r_qua_len.ensure(recs * 2 + 16)); CK(sl.r_dna_len.ensure(recs * 2 + 16));
     CK(sl.qcat.ensure(syms)); CK(sl.dcat.ensure(syms)); CK(sl.streams.ensure(titles + 16));
-    CK(sl.ftab.ensure((u64)DEC_POOL_NODES * 8 * n));
+    CK(sl.ftab.ensure((u64)pool_nodes * 8 * n));
     const bool rcq = ctx->cs.quality_order > 0, rcd = ctx->cs.dna_order > 0;
     if (rcq || rcd) CK(ctx->dec_arena.ensure(arena_bytes * n));
     ws.rec.title_off = (u32*)sl.r_title_off.p; ws.rec.seq_off = (u32*)sl.r_seq_off.p; ws.rec.qcat_off = (u32*)sl.r_qcat_off.p; ws.rec.dcat_off = (u32*)sl.r_dcat_off.p;
     ws.rec.title_len = (u16*)sl.r_title_len.p; ws.rec.qua_len = (u16*)sl.r_qua_len.p; ws.rec.dna_len = (u16*)sl.r_dna_len.p;
     ws.qcat = (u8*)sl.qcat.p; ws.dcat = (u8*)sl.dcat.p; ws.streams = (u8*)sl.streams.p;
     CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
-    { KTimer t(ctx, &sl, K_DECODE); launch_dec_tags(ws, s, sl.ftab.p, DEC_POOL_NODES); }
+    { KTimer t(ctx, &sl, K_DEC_TAGS); launch_dec_tags(ws, s, sl.ftab.p, pool_nodes); }
     if (rcq) CK(cudaMemsetAsync(ctx->dec_arena.p, 0, arena_bytes * n, s));
-    { KTimer t(ctx, &sl, K_DECODE); launch_dec_quality(ws, s, sl.ftab.p, DEC_POOL_NODES, (u8*)ctx->dec_arena.p, arena_bytes, arena_bytes); }
+    { KTimer t(ctx, &sl, K_DEC_Q); launch_dec_quality(ws, s, sl.ftab.p, pool_nodes, (u8*)ctx->dec_arena.p, arena_bytes, arena_bytes); }
     if (rcd) CK(cudaMemsetAsync(ctx->dec_arena.p, 0, arena_bytes * n, s));
-    { KTimer t(ctx, &sl, K_DECODE); launch_dec_dna(ws, s, sl.ftab.p, DEC_POOL_NODES, (u8*)ctx->dec_arena.p, arena_bytes, arena_bytes); }
-    { KTimer t(ctx, &sl, K_DECODE); launch_dec_assemble(ws, s); }
+    { KTimer t(ctx, &sl, K_DEC_D); launch_dec_dna(ws, s, sl.ftab.p, pool_nodes, (u8*)ctx->dec_arena.p, arena_bytes, arena_bytes); }
+    { KTimer t(ctx, &sl, K_DEC_ASM); launch_dec_assemble(ws, s); }
     CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -515,8 +514,16 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
     u64 big = 4ull << 20;
     if (ctx->cs.quality_order == 2) big = 64ull << 20;
     if (ctx->cs.dna_order) { const u32 o = ctx->cs.dna_order, o8 = o > 7 ? 7 : o; big = std::max<u64>(big, std::max<u64>((1ull << (2 * o)) * 8, (1ull << (3 * o8)) * 16)); }
-    const u64 small = 4ull << 20, budget = 16ull << 30;
-    const u32 per_batch = (u32)std::max<u64>(1, std::min<u64>(ctx->max_inflight, budget / small));
+    // chain arenas come in tiers: every block is first decoded with a small context hash (many chains in flight -- the chains
+    // are latency bound, so throughput is the number of chains); a chain that fills its hash retries in the next tier
+    u64 tier0 = 512ull << 10;
+    if (const char* e = getenv("DSRCGPU_DEC_ARENA_KB")) tier0 = std::max<u64>(64, (u64)atoll(e)) << 10;
+    const u64 tiers[3] = {tier0, std::max<u64>(tier0, 8ull << 20), std::max<u64>(big, 8ull << 20)};
+    const u32 pools[3] = {8192u, 65536u, 262144u};        // Huffman nodes (8 B) per block
+    const u64 small = tiers[0], budget = 16ull << 30;
+    u32 dec_batch = 32768;
+    if (const char* e = getenv("DSRCGPU_DEC_BATCH")) dec_batch = (u32)std::max(1, atoi(e));
+    const u32 per_batch = (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / small));
     std::vector<u32> idx, status, sizes, retry; std::vector<u64> offs, ooffs;
     u64 out_pos = 0;
     for (u32 first = 0; first < n; first += per_batch) {
@@ -567,21 +574,28 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
             CK(cudaStreamSynchronize(sl.stream));
             for (u32 i = 0; i < cnt; ++i) { ooffs[i] = out_pos + batch_bytes; batch_bytes += sl.h_probe[i].n_fields ? sl.h_probe[i].n_fields : 1; }
         }
-        int rc = decode_batch(ctx, sl, d_in, idx.data(), offs.data(), blk_len, ooffs.data(), cnt, d_out, cap, small, status.data(), sizes.data());
+        int rc = decode_batch(ctx, sl, d_in, idx.data(), offs.data(), blk_len, ooffs.data(), cnt, d_out, cap, small, pools[0], status.data(), sizes.data());
         if (rc) return rc;
         retry.clear();
         for (u32 i = 0; i < cnt; ++i) {
             if (status[i] == DEC_ST_RETRY) { retry.push_back(i); continue; }
             if (status[i] != ST_OK) { int e = status_to_error(ctx, status[i], first + i); if (e == DSRCGPU_E_MALFORMED) ctx->err += " (corrupt compressed block)"; return e; }
         }
-        const u32 group = (u32)std::max<u64>(1, budget / big);
-        for (size_t g0 = 0; g0 < retry.size(); g0 += group) {
-            const u32 gn = (u32)std::min<size_t>(group, retry.size() - g0);
-            std::vector<u32> gi(gn), gs(gn), gz(gn); std::vector<u64> go(gn), goo(gn);
-            for (u32 k = 0; k < gn; ++k) { const u32 i = retry[g0 + k]; gi[k] = first + i; go[k] = offs[i]; goo[k] = ooffs[i]; }
-            rc = decode_batch(ctx, sl, d_in, gi.data(), go.data(), blk_len, goo.data(), gn, d_out, cap, big, gs.data(), gz.data());
-            if (rc) return rc;
-            for (u32 k = 0; k < gn; ++k) if (gs[k] != ST_OK) return status_to_error(ctx, gs[k], gi[k]);
+        for (int tier = 1; tier < 3 && !retry.empty(); ++tier) {
+            const u32 group = (u32)std::max<u64>(1, budget / (tiers[tier] + (u64)pools[tier] * 8));
+            std::vector<u32> again;
+            for (size_t g0 = 0; g0 < retry.size(); g0 += group) {
+                const u32 gn = (u32)std::min<size_t>(group, retry.size() - g0);
+                std::vector<u32> gi(gn), gs(gn), gz(gn); std::vector<u64> go(gn), goo(gn);
+                for (u32 k = 0; k < gn; ++k) { const u32 i = retry[g0 + k]; gi[k] = first + i; go[k] = offs[i]; goo[k] = ooffs[i]; }
+                rc = decode_batch(ctx, sl, d_in, gi.data(), go.data(), blk_len, goo.data(), gn, d_out, cap, tiers[tier], pools[tier], gs.data(), gz.data());
+                if (rc) return rc;
+                for (u32 k = 0; k < gn; ++k) {
+                    if (gs[k] == DEC_ST_RETRY && tier < 2) again.push_back(retry[g0 + k]);
+                    else if (gs[k] != ST_OK) return status_to_error(ctx, gs[k], gi[k]);
+                }
+            }
+            retry.swap(again);
         }
         for (u32 i = 0; i < cnt; ++i) out_sizes[first + i] = sizes[i];
         if (!on_device) {
@@ -605,6 +619,22 @@ extern "C" int dsrcgpu_decode_blocks_device(dsrcgpu_ctx* ctx, const uint8_t* d_d
                                             uint32_t n, uint8_t* d_fastq_out, uint64_t out_cap, uint64_t* out_sizes)
 {
     return decode_impl(ctx, d_dsrc, true, blk_off, blk_len, n, d_fastq_out, out_cap, out_sizes);
+}
+
+extern "C" int dsrcgpu_release_workspace(dsrcgpu_ctx* ctx)
+{
+    if (!ctx) return DSRCGPU_E_ARG;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < ctx->n_slots; ++i) {
+        Slot& sl = ctx->slots[i];
+        CK(cudaStreamSynchronize(sl.stream));
+        DevBuf* bufs[] = {&sl.in, &sl.desc, &sl.state, &sl.result, &sl.probe, &sl.lines, &sl.qcat, &sl.dcat, &sl.trip_q, &sl.trip_d, &sl.ftab, &sl.streams, &sl.out,
+                          &sl.r_title_off, &sl.r_seq_off, &sl.r_qua_off, &sl.r_title_len, &sl.r_qua_len, &sl.r_dna_len, &sl.r_trunc_len, &sl.r_qcat_off, &sl.r_dcat_off,
+                          &sl.elem_a, &sl.elem_b, &sl.tagpool, &sl.q0_arena, &sl.tab};
+        for (DevBuf* b : bufs) b->release();
+    }
+    ctx->dec_arena.release();
+    return DSRCGPU_OK;
 }
 
 extern "C" float dsrcgpu_last_call_ms(dsrcgpu_ctx* ctx) { return ctx ? ctx->call_ms : 0.f; }

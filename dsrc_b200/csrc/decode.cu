@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_tags(Workspace ws, uint2* pool_
             r.flush();
             const u32 lim = f.max_len < TAG_STAT_LEN ? f.max_len : TAG_STAT_LEN;
             u32* roots = np.words(TAG_STAT_LEN + 1);
-            if (!roots) { status = ST_UNSUPPORTED; break; }
+            if (!roots) { status = ST_RETRY; break; }
             f.hl = (u32)(roots - (u32*)np.nodes);
             for (u32 j = 0; j <= TAG_STAT_LEN; ++j) roots[j] = 0xFFFFFFFFu;
             for (u32 j = 0; j < lim; ++j) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_tags(Workspace ws, uint2* pool_
         for (u32 i = 0; i < 128; ++i) if (r.bit()) symbols[nsym++] = (u8)i;
         raw_root = np.load(r);
     }
-    if (np.ovf && status == ST_OK) status = ST_UNSUPPORTED;
+    if (np.ovf && (status == ST_OK || status == ST_MALFORMED)) status = r.ovr ? ST_MALFORMED : ST_RETRY;
     if (r.ovr && status == ST_OK) status = ST_MALFORMED;
 
     const u32* pw = (const u32*)np.nodes;
@@ -265,24 +265,24 @@ struct RowStore {
         u32 lg = 0; while (((u64)sb << (lg + 1)) <= arena_bytes) ++lg;
         mask = (1u << lg) - 1; shift = 32 - lg; limit = (u32)(((u64)1 << lg) * 7 / 8);
     }
-    __device__ u16* row(u32 ctx, u32 N)
+    // returns the row of ctx; fresh = the row has not been touched by this block (contents undefined: treat as all ones)
+    __device__ __forceinline__ u16* row(u32 ctx, bool& fresh)
     {
         if (direct) {
             u16* p = (u16*)(base + (u64)ctx * slot_bytes);
-            if (p[0] == 0) for (u32 i = 0; i < N; ++i) p[i] = 1;
+            fresh = p[0] == 0;                              // counters never drop below 1; the arena is zeroed per batch
             return p;
         }
         u32 h = (ctx * 0x9E3779B1u) >> shift;
         for (;;) {
             u8* s = base + (u64)h * slot_bytes;
+            if (row_off >= 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(s + row_off));   // row sector in flight together with the key sector
             const u32 key = *(u32*)s;
-            if (key == ctx + 1) return (u16*)(s + row_off);
+            if (key == ctx + 1) { fresh = false; return (u16*)(s + row_off); }
             if (key == 0) {
-                if (used >= limit) { fail = true; return (u16*)(s + row_off); }
-                *(u32*)s = ctx + 1; ++used;
-                u16* p = (u16*)(s + row_off);
-                for (u32 i = 0; i < N; ++i) p[i] = 1;
-                return p;
+                if (used >= limit) fail = true; else { *(u32*)s = ctx + 1; ++used; }
+                fresh = true;
+                return (u16*)(s + row_off);
             }
             h = (h + 1) & mask;
         }
@@ -292,29 +292,94 @@ struct RowStore {
 struct RcDec {                     // RangeDecoder (src/RangeCoder.h:98-134)
     u64 low, buffer; u32 range; BitR* r;
     __device__ void start(BitR* r_) { r = r_; buffer = 0; for (u32 i = 1; i <= 8; ++i) buffer |= (u64)r->byte() << (64 - i * 8); low = 0; range = 0xFFFFFFFFu; }
-    // TSymbolCoderRC<N>::DecodeSymbol (src/SymbolCoderRC.h:50-63) on row st
-    __device__ u32 decode(u16* stt, u32 N)
+    // GetCumulativeFreq: a valid stream keeps buffer below the old range, so the quotient is a 32-bit division
+    __device__ __forceinline__ u32 cum(u32 tot)
     {
-        u32 tot = 0;
-        for (u32 i = 0; i < N; ++i) tot += stt[i];
-        if (tot >= (1u << 16) - 2 * N) { tot = 0; for (u32 i = 0; i < N; ++i) { const u32 c = stt[i] - (stt[i] >> 1); stt[i] = (u16)c; tot += c; } }
         range /= tot;
-        const u32 cul = (u32)(buffer / range);
-        u32 idx = 0, hi = 0;
-        for (;; ++idx) { hi += stt[idx]; if (hi > cul || idx + 1 >= N) break; }
-        const u32 f = stt[idx];
-        hi -= f;
-        const u32 rr = hi * range;
+        return (buffer >> 32) ? (u32)(buffer / range) : (u32)buffer / range;
+    }
+    __device__ __forceinline__ void update(u32 f, u32 lo)
+    {
+        const u32 rr = lo * range;
         buffer -= rr; low += rr; range *= f;
         while (range <= 0x00FFFFFFu) {
             if ((low ^ (low + range)) & 0xFF00000000000000ull) { const u32 q = (u32)low; range = (q | 0x00FFFFFFu) - q; }
             buffer = (buffer << 8) + r->byte();
             low <<= 8; range <<= 8;
         }
-        stt[idx] = (u16)(f + 2);
-        return idx;
     }
 };
+
+// TSymbolCoderRC<N>::DecodeSymbol (src/SymbolCoderRC.h:50-63) on the row at p. Small rows are held in registers as packed
+// u16 pairs (vector load, one 2-byte store back unless the row was fresh or rescaled); larger rows are walked in memory.
+template <int N>
+__device__ __forceinline__ u32 rc_decode_row(RcDec& rc, u16* p, bool fresh)
+{
+    u32 c[N / 2];
+    if (fresh) {
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) c[k] = 0x00010001u;
+    } else if (N == 4) { const uint2 v = *(const uint2*)p; c[0] = v.x; c[1] = v.y; }
+    else {
+#pragma unroll
+        for (int k = 0; k < N / 8; ++k) { const uint4 v = ((const uint4*)p)[k]; c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w; }
+    }
+    u32 tot = 0;
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) tot += (c[k] & 0xFFFFu) + (c[k] >> 16);
+    bool whole = fresh;
+    if (tot >= (1u << 16) - 2 * N) {
+        tot = 0; whole = true;
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) { u32 lo = c[k] & 0xFFFFu, hi = c[k] >> 16; lo -= lo >> 1; hi -= hi >> 1; c[k] = lo | (hi << 16); tot += lo + hi; }
+    }
+    const u32 cul = rc.cum(tot);
+    u32 idx = N - 1, f = 0, hi = 0, acc = 0; bool found = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const u32 v = (c[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+        acc += v;
+        const bool hit = !found && (acc > cul || k == N - 1);
+        if (hit) { idx = k; f = v; hi = acc - v; found = true; }
+    }
+    rc.update(f, hi);
+    if (whole) {
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) c[k] += (u32)k == (idx >> 1) ? (2u << ((idx & 1) * 16)) : 0u;
+        if (N == 4) *(uint2*)p = make_uint2(c[0], c[1]);
+        else {
+#pragma unroll
+            for (int k = 0; k < N / 8; ++k) ((uint4*)p)[k] = make_uint4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
+        }
+    } else p[idx] = (u16)(f + 2);
+    return idx;
+}
+__device__ u32 rc_decode_row_mem(RcDec& rc, u16* stt, u32 N, bool fresh)
+{
+    if (fresh) for (u32 i = 0; i < N; ++i) stt[i] = 1;
+    u32 tot = 0;
+    for (u32 i = 0; i < N; i += 8) {
+        const uint4 v = *(const uint4*)(stt + i);
+        tot += (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) + (v.w & 0xFFFFu) + (v.w >> 16);
+    }
+    if (tot >= (1u << 16) - 2 * N) { tot = 0; for (u32 i = 0; i < N; ++i) { const u32 c = stt[i] - (stt[i] >> 1); stt[i] = (u16)c; tot += c; } }
+    const u32 cul = rc.cum(tot);
+    u32 idx = 0, hi = 0;
+    for (;; ++idx) { hi += stt[idx]; if (hi > cul || idx + 1 >= N) break; }
+    const u32 f = stt[idx];
+    rc.update(f, hi - f);
+    stt[idx] = (u16)(f + 2);
+    return idx;
+}
+__device__ __forceinline__ u32 rc_decode_any(RcDec& rc, u16* p, u32 N, bool fresh)
+{
+    switch (N) {
+    case 4: return rc_decode_row<4>(rc, p, fresh);
+    case 8: return rc_decode_row<8>(rc, p, fresh);
+    case 16: return rc_decode_row<16>(rc, p, fresh);
+    default: return rc_decode_row_mem(rc, p, N, fresh);
+    }
+}
 
 // template arguments per scheme (src/QualityModelerProxy.h:231-254)
 __device__ __forceinline__ bool dec_quality_cfg(u32 order, u32 scheme, u32& alpha, u32& bits, u32& so, u32& rescale)
@@ -367,9 +432,10 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_quality(Workspace ws, uint2* po
             u32 nc = 0, acc = 0, pctx = 0;                 // pctx = j * rescale / len, kept incrementally
             for (u32 j = 0; j < len; ++j) {
                 const u32 ctx = (u32)(((hash & hash_mask) << bits) | pctx);
-                u16* row = rs.row(ctx, alpha);
+                bool fresh;
+                u16* row = rs.row(ctx, fresh);
                 if (rs.fail) break;
-                const u32 sym = rc.decode(row, alpha);
+                const u32 sym = rc_decode_any(rc, row, alpha, fresh);
                 hash <<= bits;
                 const u64 next = (hash >> bits_lo) & sym_mask;
                 const u64 swp = (next + sym_buf) / 2;
@@ -393,9 +459,9 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_quality(Workspace ws, uint2* po
         for (u32 i = 0; i < 256; ++i) if (r.bit()) symbols[nsym++] = (u8)i;
         if (L > 65535) { st.status = ST_MALFORMED; return; }
         u32* roots = np.words(L ? L : 1);
-        if (!roots) { st.status = ST_UNSUPPORTED; return; }
+        if (!roots) { st.status = ST_RETRY; return; }
         for (u32 j = 0; j < L && !np.ovf; ++j) roots[j] = np.load(r);
-        if (np.ovf) { st.status = ST_UNSUPPORTED; return; }
+        if (np.ovf) { st.status = r.ovr ? ST_MALFORMED : ST_RETRY; return; }
         const u32 max_bits = dsrc_bit_length((u64)L);
         const bool variable = truncated ? r.bit() != 0 : false;
         for (u32 k = 0; k < n && !r.ovr; ++k) {
@@ -423,9 +489,9 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_quality(Workspace ws, uint2* po
         u8 lb = 0, le = 0;
         if (nq > 1) {
             qroot = np.words(nq); lroot = np.words(nq);
-            if (!qroot || !lroot) { st.status = ST_UNSUPPORTED; return; }
+            if (!qroot || !lroot) { st.status = ST_RETRY; return; }
             for (u32 i = 0; i < nq && !np.ovf; ++i) { qroot[i] = np.load(r); lroot[i] = np.load(r); }
-            if (np.ovf) { st.status = ST_UNSUPPORTED; return; }
+            if (np.ovf) { st.status = r.ovr ? ST_MALFORMED : ST_RETRY; return; }
             r.flush();
         } else {
             r.flush();
@@ -485,7 +551,7 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_dna(Workspace ws, uint2* pool_b
             for (u32 i = 0; i < 20; ++i) symbols[i] = 255;
             for (u32 i = 0; i < 20; ++i) if (r.bit()) symbols[ns++] = (u8)i;
             const u32 root = np.load(r);
-            if (np.ovf) status = ST_UNSUPPORTED;
+            if (np.ovf) status = r.ovr ? ST_MALFORMED : ST_RETRY;
             for (u32 i = 0; i < M && !r.ovr && status == ST_OK; ++i) dc[i] = symbols[np.get(root, r) % 20];
             r.flush();
         }
@@ -497,9 +563,10 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_dna(Workspace ws, uint2* pool_b
         RcDec rc; rc.start(&r);
         u32 hash = 0;
         for (u32 i = 0; i < M && !r.ovr; ++i) {
-            u16* row = rs.row(hash, alpha);
+            bool fresh;
+            u16* row = rs.row(hash, fresh);
             if (rs.fail) break;
-            const u32 sym = rc.decode(row, alpha);
+            const u32 sym = rc_decode_any(rc, row, alpha, fresh);
             dc[i] = (u8)sym;
             hash = ((hash << bits) | sym) & mask;
         }

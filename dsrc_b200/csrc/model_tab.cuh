@@ -12,8 +12,12 @@
 
 #define TT 2048                               // symbols per tile
 #define TT_SHIFT 11
+#ifndef TAB_C1
 #define TAB_C1 6
+#endif
+#ifndef TAB_LONG
 #define TAB_LONG 24                           // groups longer than this take a whole warp
+#endif
 
 struct TabShared {
     u32 el[2][TT];                            // (ctx << 11) | position in tile, ping-pong of the in-tile sort

@@ -17,12 +17,51 @@ __device__ __forceinline__ bool is_term(const u8* b, u32 p)
     return c == '\r' || (c == '\n' && !(p > 0 && b[p - 1] == '\r'));
 }
 
+// Terminator scan over 16-byte aligned chunks. Chunk c of a block covers block positions [16c - mis, 16c - mis + 16) where
+// mis = misalignment of the block start; term_mask() returns one bit per byte of the chunk (bit k = byte k terminates a line)
+// and the CR bytes among them, using the byte-wise SIMD compares. prev_cr: the byte before the chunk is '\r'.
+struct ChunkScan {
+    const u8* base; u32 mis, len;                    // base = block start rounded down to 16 bytes
+    __device__ __forceinline__ void init(const u8* b, u32 in_len) { mis = (u32)((uintptr_t)b & 15u); base = b - mis; len = in_len; }
+    __device__ __forceinline__ u32 n_chunks() const { return (len + mis + 15) / 16; }
+    // valid-byte mask of chunk c (bits of positions inside [0, len))
+    __device__ __forceinline__ u32 valid(u32 c) const
+    {
+        const i32 lo = (i32)(16 * c) - (i32)mis;       // block position of byte 0
+        u32 m = 0xFFFFu;
+        if (lo < 0) m &= 0xFFFFu << (u32)(-lo);
+        if ((u32)(lo + 16) > len) m &= 0xFFFFu >> (u32)(lo + 16 - (i32)len);
+        return m;
+    }
+    __device__ __forceinline__ void masks(u32 c, u32& term, u32& cr) const
+    {
+        const uint4 v = *(const uint4*)(base + 16 * (u64)c);
+        const u32 w[4] = {v.x, v.y, v.z, v.w};
+        u32 crm = 0, nlm = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 a = __vcmpeq4(w[k], 0x0D0D0D0Du) & 0x01010101u, n = __vcmpeq4(w[k], 0x0A0A0A0Au) & 0x01010101u;
+            // gather the 4 flag bits (bit 0 of every byte) into a nibble
+            crm |= (((a * 0x00204081u) >> 21) & 0xFu) << (4 * k);   // bits 0,8,16,24 -> 0..3
+            nlm |= (((n * 0x00204081u) >> 21) & 0xFu) << (4 * k);
+        }
+        const u32 vm = valid(c);
+        crm &= vm; nlm &= vm;
+        u32 prev = (crm << 1) & 0xFFFFu;
+        const i32 lo = (i32)(16 * c) - (i32)mis;
+        if (lo > 0 && base[16 * (u64)c - 1] == '\r') prev |= 1u;
+        term = crm | (nlm & ~prev); cr = crm;
+    }
+};
+
 __global__ void __launch_bounds__(DSRC_CTA) k_count_lines(Workspace ws)
 {
     const BlockDesc& d = ws.desc[blockIdx.x];
     const u8* b = ws.in + d.in_off;
+    ChunkScan cs; cs.init(b, d.in_len);
+    const u32 nc = cs.n_chunks();
     u32 cnt = 0;
-    for (u32 p = threadIdx.x; p < d.in_len; p += DSRC_CTA) cnt += is_term(b, p);
+    for (u32 c = threadIdx.x; c < nc; c += DSRC_CTA) { u32 t, cr; cs.masks(c, t, cr); cnt += __popc(t); }
     cnt = warp_red_sum(cnt);
     __shared__ u32 sm[DSRC_WARPS];
     if (lane_id() == 0) sm[warp_id()] = cnt;
@@ -44,6 +83,7 @@ __global__ void __launch_bounds__(DSRC_CTA) k_count_lines(Workspace ws)
     }
 }
 
+#define PARSE_CH 4                                   // consecutive 16-byte chunks per thread and step
 __global__ void __launch_bounds__(DSRC_CTA) k_parse(Workspace ws)
 {
     const BlockDesc& d = ws.desc[blockIdx.x];
@@ -57,19 +97,29 @@ __global__ void __launch_bounds__(DSRC_CTA) k_parse(Workspace ws)
     __syncthreads();
     // phase A: positions of all terminators, in order. lines[k] = position | (CRLF ? 1<<31 : 0)
     u32 skipped = 0;
-    for (u32 base = 0; base < d.in_len; base += DSRC_CTA) {
-        u32 p = base + threadIdx.x;
-        bool t = p < d.in_len && is_term(b, p);
-        u32 total, ex = block_excl_sum(t ? 1u : 0u, sm, &total);
-        u32 carry = s_carry;
-        if (t) {
-            bool crlf = b[p] == '\r' && p + 1 < d.in_len && b[p + 1] == '\n';
-            skipped += crlf;
-            u32 k = carry + ex;
-            if (k < d.line_cap) lines[k] = p | (crlf ? 0x80000000u : 0u);
+    ChunkScan cs; cs.init(b, d.in_len);
+    const u32 nc = cs.n_chunks();
+    for (u32 c0 = 0; c0 < nc; c0 += DSRC_CTA * PARSE_CH) {
+        u32 tm[PARSE_CH], crm[PARSE_CH], cnt = 0;
+        const u32 cb = c0 + threadIdx.x * PARSE_CH;
+#pragma unroll
+        for (int k = 0; k < PARSE_CH; ++k) { tm[k] = 0; crm[k] = 0; if (cb + k < nc) cs.masks(cb + k, tm[k], crm[k]); cnt += __popc(tm[k]); }
+        u32 total, ex = block_excl_sum(cnt, sm, &total);
+        u32 kq = s_carry + ex;
+#pragma unroll
+        for (int k = 0; k < PARSE_CH; ++k) {
+            u32 m = tm[k];
+            while (m) {
+                const u32 bit = __ffs(m) - 1; m &= m - 1;
+                const u32 p = 16 * (cb + k) + bit - cs.mis;
+                const bool crlf = ((crm[k] >> bit) & 1u) && p + 1 < d.in_len && b[p + 1] == '\n';
+                skipped += crlf;
+                if (kq < d.line_cap) lines[kq] = p | (crlf ? 0x80000000u : 0u);
+                ++kq;
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + total;
+        if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
     }
     skipped = warp_red_sum(skipped);
@@ -144,6 +194,8 @@ __global__ void __launch_bounds__(DSRC_CTA) k_preprocess(Workspace ws)
     __shared__ u32 s_qf[DSRC_WARPS][256];
     __shared__ u32 s_df[DSRC_WARPS][20];
     __shared__ u32 s_min, s_max, s_th, s_rle, s_bad;
+    __shared__ u8 s_lut[256];                          // dnaToIndexTable, once per CTA
+    s_lut[threadIdx.x] = (u8)dna_index((u8)threadIdx.x);
     for (u32 i = threadIdx.x; i < DSRC_WARPS * 256; i += DSRC_CTA) (&s_qf[0][0])[i] = 0;
     for (u32 i = threadIdx.x; i < DSRC_WARPS * 20; i += DSRC_CTA) (&s_df[0][0])[i] = 0;
     if (threadIdx.x == 0) { s_carry = 0; s_min = 0xFFFFFFFFu; s_max = 0; s_th = 0; s_rle = 0; s_bad = 0; }
@@ -176,7 +228,7 @@ __global__ void __launch_bounds__(DSRC_CTA) k_preprocess(Workspace ws)
         u32 kept = 0, th = 0, rle = 0; u32 last_q = 255;
         for (u32 j0 = 0; j0 < len; j0 += 32) {
             u32 j = j0 + ln; bool in = j < len;
-            u32 s = in ? dna_index(seq[j]) : 0;
+            u32 s = in ? s_lut[seq[j]] : 0;
             u32 q = in ? (u8)(qua[j] - ws.qoff) : 0;
             bool moved = in && s > 3 && q < 7;                    // RecordsProcessor.cpp:228-233
             if (moved) q = (u8)(q + (128 + ((s - 3 + 1) << 3) - 16));
@@ -223,7 +275,7 @@ __global__ void __launch_bounds__(DSRC_CTA) k_preprocess(Workspace ws)
         u32 base = 0;
         for (u32 j0 = 0; j0 < len; j0 += 32) {
             u32 j = j0 + ln; bool in = j < len;
-            u32 s = in ? dna_index(seq[j]) : 0;
+            u32 s = in ? s_lut[seq[j]] : 0;
             u32 q = in ? (u8)(qua[j] - ws.qoff) : 0;
             bool keep = in && !(s > 3 && q < 7);
             u32 m = __ballot_sync(0xFFFFFFFFu, keep);

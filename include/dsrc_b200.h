@@ -113,6 +113,9 @@ void dsrcgpu_set_profiling(dsrcgpu_ctx* ctx, int on);
 /* copies the 64 phase counters accumulated since the last reset */
 int dsrcgpu_phase_cycles(dsrcgpu_ctx* ctx, uint64_t* out64, int reset);
 
+/* frees the internal device workspaces (they are re-created on demand by the next encode/decode call) */
+int dsrcgpu_release_workspace(dsrcgpu_ctx* ctx);
+
 /* Device allocation helpers so a host language without a CUDA binding can stage resident inputs. */
 int dsrcgpu_device_alloc(dsrcgpu_ctx* ctx, uint64_t bytes, void** d_ptr);
 int dsrcgpu_device_free(dsrcgpu_ctx* ctx, void* d_ptr);
