@@ -332,10 +332,24 @@ def main():
         "rc_encode": 2 * syms * 8 + int(comp[:, 2].sum() + comp[:, 3].sum()),
         "meta_sizes": n * 64, "gather": 2 * comp_bytes,
     }
+    # measured DRAM traffic per launch of the dominant kernel, from the committed `ncu --set full` capture of this command
+    traffic = None
+    try:
+        import csv
+        kmap = {"model_quality": "k_model<1>", "model_dna": "k_model<0>"}
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_bench_model_full.csv"))))
+        h = rows[0]
+        for r in rows[2:]:
+            if kmap.get(dom[0], "?") in r[0]:
+                traffic = (float(r[h.index("dram__bytes_read.sum")]) + float(r[h.index("dram__bytes_write.sum")])) * 1e9
+    except Exception:
+        traffic = None
     dom_ms_per_step = dom[1][0] / args.steps
     ach = alg.get(dom[0], 0) / (dom_ms_per_step / 1e3) / 1e9 if dom_ms_per_step > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg.get(dom[0], 0) / max(1, dom[1][1] // max(1, args.steps)),
+                "note": "kernel times are CUDA-event pairs on the launching stream; with 3 batches in flight they include time shared with other streams' kernels",
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktot.items()},
                 "launches_per_kernel_per_step": max(1, dom[1][1] // max(1, args.steps)),
                 "block_path_compulsory_frac": (payload + comp_bytes) / step_s / 1e9 / peak,
@@ -344,7 +358,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdsrcref.so")):
         threads = os.cpu_count() or 1
-        ns = min(n, threads * 100)
+        ns = min(n, threads * 1500)      # ~10-20 s of CPU work
         r, dt, tot = reference_cpu_rate(hp, offs, lens, ns, threads)
         cpu = {"value": r, "unit": "MB/s", "cores": threads, "kind": "reference",
                "sample": "first %d blocks (%.1f MB) of the workload, reference BlockCompressor::Store, one instance per thread, %.1f s" % (ns, tot / 1e6, dt)}
