@@ -191,14 +191,31 @@ def main():
     d_in = torch.empty(in_bytes, dtype=torch.uint8, device="cuda")
     nb = C.c_uint64()
     check(L.dsrcgpu_synth_fastq_device(ctx, args.profile, 99, rank * n_reads, n_reads, C.c_void_p(d_in.data_ptr()), in_bytes, C.byref(nb)), "synth")
-    h_in = torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True)
-    h_in.copy_(d_in)
-    torch.cuda.synchronize()
-    hp = h_in.data_ptr()
-    n = L.dsrcgpu_cut_blocks(C.c_void_p(hp), in_bytes, BLOCK_BYTES, None, None, 0)
-    offs = np.zeros(n, dtype=np.uint64)
-    lens = np.zeros(n, dtype=np.uint32)
-    L.dsrcgpu_cut_blocks(C.c_void_p(hp), in_bytes, BLOCK_BYTES, offs.ctypes.data_as(_lib.u64p), lens.ctypes.data_as(_lib.u32p), n)
+    # block cut (a host function: IFastqStreamReader::ReadNextChunk) over a sliding pinned window of the device-resident shard --
+    # a full host copy per rank would not fit the box's RAM at 8 ranks
+    WIN = min(in_bytes, 512 << 20)
+    win = torch.empty(WIN, dtype=torch.uint8, pin_memory=True)
+    cap_blocks = WIN // (BLOCK_BYTES - 8192) + 8
+    woff = np.zeros(cap_blocks, dtype=np.uint64)
+    wlen = np.zeros(cap_blocks, dtype=np.uint32)
+    offs_l, lens_l = [], []
+    start = 0
+    while start < in_bytes:
+        w = min(WIN, in_bytes - start)
+        win[:w].copy_(d_in[start:start + w])
+        torch.cuda.synchronize()
+        k = int(L.dsrcgpu_cut_blocks(C.c_void_p(win.data_ptr()), w, BLOCK_BYTES, woff.ctypes.data_as(_lib.u64p), wlen.ctypes.data_as(_lib.u32p), cap_blocks))
+        last = start + w == in_bytes
+        take = k if last else k - 1              # the window's final block was cut at the window end, not at a record boundary rule
+        if take <= 0:
+            raise SystemExit("bench.py: cut window too small")
+        offs_l.append(woff[:take] + np.uint64(start))
+        lens_l.append(wlen[:take].copy())
+        start = in_bytes if last else start + int(woff[take])
+    del win
+    offs = np.ascontiguousarray(np.concatenate(offs_l), dtype=np.uint64)
+    lens = np.ascontiguousarray(np.concatenate(lens_l), dtype=np.uint32)
+    n = len(offs)
     payload = int(lens.astype(np.uint64).sum())
     out_cap = in_bytes // 2 + (1 << 20)
     d_out = torch.empty(out_cap, dtype=torch.uint8, device="cuda")
@@ -241,7 +258,7 @@ def main():
                                              None, k, C.c_void_p(d_out.data_ptr()), out_cap, so.ctypes.data_as(_lib.u32p), None, None), "parity encode")
         got = d_out[:int(so.sum())].cpu().numpy().tobytes()
         p = 0
-        hv = h_in.numpy()
+        hv = d_in[:int(offs[k - 1]) + int(lens[k - 1])].cpu().numpy()
         ora.store(hv[int(offs[0]):int(offs[0]) + int(lens[0])].tobytes())       # warm the oracle's field vector like blk_tagcap=NULL does
         for i in range(k):
             exp, _, _ = ora.store(hv[int(offs[i]):int(offs[i]) + int(lens[i])].tobytes())
@@ -278,11 +295,30 @@ def main():
     # e2e through the host-buffer call
     e2e = None
     if not args.no_e2e:
-        h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
+        # pinned host staging is bounded by the box's RAM shared between the ranks: the e2e leg runs on the first ne blocks
+        try:
+            import psutil
+            host_total = psutil.virtual_memory().total
+        except Exception:
+            host_total = 64 << 30
+        budget = int(host_total * 0.5 / max(1, world))
+        ne = n
+        if in_bytes + out_cap > budget:
+            ends = offs + lens.astype(np.uint64)
+            ne = max(1, int(np.searchsorted(ends, np.uint64(budget * 2 // 3), side="right")))
+        e_in = int(offs[ne - 1]) + int(lens[ne - 1])
+        e_payload = int(lens[:ne].astype(np.uint64).sum())
+        e_cap = e_in // 2 + (1 << 20)
+        h_in = torch.empty(e_in, dtype=torch.uint8, pin_memory=True)
+        h_in.copy_(d_in[:e_in])
+        torch.cuda.synchronize()
+        hp = h_in.data_ptr()
+        h_out = torch.empty(e_cap, dtype=torch.uint8, pin_memory=True)
+        esz = np.zeros(ne, dtype=np.uint32)
 
         def step_host():
-            check(L.dsrcgpu_encode_blocks(ctx, C.c_void_p(hp), offs.ctypes.data_as(_lib.u64p), lens.ctypes.data_as(_lib.u32p), None, n,
-                                          C.c_void_p(h_out.data_ptr()), out_cap, sizes.ctypes.data_as(_lib.u32p), None, None), "encode_host")
+            check(L.dsrcgpu_encode_blocks(ctx, C.c_void_p(hp), offs.ctypes.data_as(_lib.u64p), lens.ctypes.data_as(_lib.u32p), None, ne,
+                                          C.c_void_p(h_out.data_ptr()), e_cap, esz.ctypes.data_as(_lib.u32p), None, None), "encode_host")
         for _ in range(max(1, min(args.warmup, 2))):
             step_host()
         barrier()
@@ -294,8 +330,10 @@ def main():
         tv = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        e2e = {"value": payload * world / (float(tv[0]) / args.steps) / 1e6, "unit": "MB/s",
-               "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(sizes.astype(np.uint64).sum())}
+        e2e = {"value": e_payload * world / (float(tv[0]) / args.steps) / 1e6, "unit": "MB/s",
+               "h2d_bytes_per_step": int(e_in), "d2h_bytes_per_step": int(esz.astype(np.uint64).sum()),
+               "blocks_per_gpu": int(ne), "note": "whole workload" if ne == n else "first %d of %d blocks per GPU (pinned staging bounded by host RAM / ranks)" % (ne, n)}
+        del h_in, h_out
     # decode leg (BASELINE configs[4], bounded sample): BlockCompressor::Read of the first blocks of the archive just written,
     # device-resident, verified byte for byte against the input
     dec = None
@@ -356,10 +394,11 @@ def main():
                 "block_path_survey_A_frac": (payload + comp_bytes + syms * 64) / step_s / 1e9 / peak}
 
     cpu = None
-    if rank == 0 and not args.no_cpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdsrcref.so")):
+    if rank == 0 and world == 1 and not args.no_cpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdsrcref.so")):
         threads = os.cpu_count() or 1
         ns = min(n, threads * 1500)      # ~10-20 s of CPU work
-        r, dt, tot = reference_cpu_rate(hp, offs, lens, ns, threads)
+        h_cpu = d_in[:int(offs[ns - 1]) + int(lens[ns - 1])].cpu().numpy()
+        r, dt, tot = reference_cpu_rate(h_cpu.ctypes.data, offs, lens, ns, threads)
         cpu = {"value": r, "unit": "MB/s", "cores": threads, "kind": "reference",
                "sample": "first %d blocks (%.1f MB) of the workload, reference BlockCompressor::Store, one instance per thread, %.1f s" % (ns, tot / 1e6, dt)}
 
