@@ -15,6 +15,9 @@
 #ifndef TAB_C1
 #define TAB_C1 6
 #endif
+#ifndef TAB_MATCH_ANY
+#define TAB_MATCH_ANY 8                       // digits this wide rank their row with match.any (few distinct values per row), narrower ones with ballots
+#endif
 #ifndef TAB_LONG
 #define TAB_LONG 24                           // groups longer than this take a whole warp
 #endif
@@ -31,6 +34,7 @@ struct TabShared {
     u16 longs[TT / (TAB_LONG + 1) + 2];
     u32 B[DSRC_WARPS][16], P[DSRC_WARPS][16];
     u32 n_heads[3], n_long, n_touched;
+    u8 plut[1024];                            // position bucket of every read position when the block's reads have one length
 };
 
 // lanes holding the same `bits`-wide digit (replaces match.any, whose cost grows with the number of distinct values)
@@ -70,8 +74,14 @@ __device__ __forceinline__ void tile_sort_pass_t(TabShared& S, u32* scan, const 
         const u32 e = in ? src[i] : 0u;
         const u32 d = (e >> shift) & dmask;
         u32 peers = __ballot_sync(FULL, in);
+#if TAB_MATCH_ANY
+        if (BITS >= TAB_MATCH_ANY) { if (in) peers = __match_any_sync(peers, d); }
+        else
+#endif
+        {
 #pragma unroll
         for (int k = 0; k < BITS; ++k) { const u32 m = __ballot_sync(FULL, (d >> k) & 1u); peers &= ((d >> k) & 1u) ? m : ~m; }
+        }
         const u32 pos = in ? H[d] + __popc(peers & lt) : 0u;
         __syncwarp();
         if (in) {

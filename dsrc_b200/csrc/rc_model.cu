@@ -87,15 +87,26 @@ struct FetchSorted {
     typedef u64 Raw;
     const u64* src;
     __device__ __forceinline__ void begin(u32) {}
-    __device__ __forceinline__ Raw ld(u32 i, bool in) const { return in ? src[i] : 0ull; }
+    __device__ __forceinline__ Raw ld(u32 i, bool in) { return in ? src[i] : 0ull; }
     __device__ __forceinline__ u64 mk(Raw r, u32, bool) { return r; }
 };
 // quality context (TQualityModelBase::UpdateHash/GetHash, QualityEncoder.h:77-94; position bucket :307)
 struct FetchQ {
     typedef u32 Raw;
     const u8* q; const u8* pctx; const u8* rank; u32 so, h, bits, M; u32 prev;
-    __device__ __forceinline__ void begin(u32 start) { const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? rank[q[j]] : 0u; }
-    __device__ __forceinline__ Raw ld(u32 i, bool in) const { return in ? ((u32)q[i] | ((u32)pctx[i] << 8)) : 0u; }
+    const u8* plut; u32 fixed_len, jpos;              // fixed_len != 0: position bucket from the shared-memory table, indexed by i % len
+    __device__ __forceinline__ void begin(u32 start)
+    {
+        const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? rank[q[j]] : 0u;
+        if (fixed_len) jpos = (start + lane_id()) % fixed_len;
+    }
+    __device__ __forceinline__ Raw ld(u32 i, bool in)
+    {
+        u32 pc;
+        if (fixed_len) { pc = plut[jpos]; jpos += 32; while (jpos >= fixed_len) jpos -= fixed_len; }
+        else pc = in ? pctx[i] : 0u;
+        return in ? ((u32)q[i] | (pc << 8)) : 0u;
+    }
     __device__ __forceinline__ u64 mk(Raw raw, u32 i, bool in)
     {
         const u32 ln = lane_id();
@@ -123,7 +134,7 @@ struct FetchD {
     typedef u32 Raw;
     const u8* sq; u32 ord, bits, M; u32 prev;
     __device__ __forceinline__ void begin(u32 start) { const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? sq[j] : 0u; }
-    __device__ __forceinline__ Raw ld(u32 i, bool in) const { return in ? sq[i] : 0u; }
+    __device__ __forceinline__ Raw ld(u32 i, bool in) { return in ? sq[i] : 0u; }
     __device__ __forceinline__ u64 mk(Raw r0, u32 i, bool in)
     {
         const u32 ln = lane_id(), mask = (1u << bits) - 1;
@@ -385,8 +396,15 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
 
         u64* const trip = (QUALITY ? ws.trip_q : ws.trip_d) + d.sym_base;
         u8* pc = (u8*)bufB;
-        if (QUALITY) {
-            // position bucket of every symbol (TTranslationalQualityEncoder::Encode :307), parked in the idle sort buffer
+        u32 fixed_len = 0;
+        const bool tabpath = cfg.alpha <= 16 && ws.tab != nullptr;
+        if (QUALITY && tabpath && st.min_len == st.max_len && st.max_len > 0 && st.max_len <= 1024) {
+            // one read length in the block: position bucket j * rescale / len (TTranslationalQualityEncoder::Encode :307) from a small table
+            fixed_len = st.max_len;
+            for (u32 j = tid; j < fixed_len; j += DSRC_CTA) TS.plut[j] = (u8)(j * cfg.rescale / fixed_len);
+            __syncthreads();
+        } else if (QUALITY) {
+            // variable lengths: the bucket of every symbol is computed per record and parked in the idle sort buffer
             const RecArrays& R = ws.rec;
             for (u32 r = warp_id(); r < st.n_rec; r += DSRC_WARPS) {
                 const u32 len = R.qua_len[d.rec_base + r], qo = R.qcat_off[d.rec_base + r];
@@ -394,11 +412,11 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
             }
             __syncthreads();
         }
-        if (cfg.alpha <= 16 && ws.tab) {
+        if (tabpath) {
             // ---- tile/table engine (model_tab.cuh)
             u8* tab = ws.tab + (u64)blockIdx.x * ws.tab_stride;
             if (QUALITY) {
-                FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M;
+                FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M; f.plut = TS.plut; f.fixed_len = fixed_len; f.jpos = 0;
                 tab_engine<16>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 16);
             } else {
                 FetchD f; f.sq = ws.dcat + d.sym_base; f.ord = cfg.ord; f.bits = cfg.bits; f.prev = 0; f.M = M;
@@ -409,7 +427,7 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
         }
         // ---- sort engine: first pass straight from the symbols (contexts are a pure function of the input), then passes over elements
         if (QUALITY) {
-            FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M;
+            FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M; f.plut = nullptr; f.fixed_len = 0; f.jpos = 0;
             sort_pass(S, f, bufA, M, 40, pbits);
         } else {
             FetchD f; f.sq = ws.dcat + d.sym_base; f.ord = cfg.ord; f.bits = cfg.bits; f.prev = 0; f.M = M;
