@@ -20,10 +20,10 @@ class DsrcGpuError(RuntimeError):
 
 class BlockCompressor:
     def __init__(self, quality_offset=33, plus_repetition=False, dna_order=0, quality_order=0,
-                 max_block_bytes=8 << 20, max_inflight_blocks=0, device=0):
+                 max_block_bytes=8 << 20, max_inflight_blocks=0, device=0, calc_crc32=False):
         self.L = _lib.lib()
         ds = _lib.Dataset(quality_offset, int(plus_repetition), 0)
-        cs = _lib.Settings(dna_order, quality_order, 0, 0, 0)
+        cs = _lib.Settings(dna_order, quality_order, 0, 0, int(calc_crc32))
         self.h = C.c_void_p()
         rc = self.L.dsrcgpu_create(C.byref(self.h), device, C.byref(ds), C.byref(cs), max_block_bytes, max_inflight_blocks)
         if rc != 0:

@@ -30,9 +30,9 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_DEC_TAGS, K_DEC_Q, K_DEC_D, K_DEC_ASM, K_NUM };
+enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_DEC_TAGS, K_DEC_Q, K_DEC_D, K_DEC_ASM, K_CRC, K_NUM };
 static const char* K_NAMES[K_NUM] = {"count_lines", "parse", "preprocess", "tags", "model_quality", "model_dna", "rc_encode",
-                                     "q0_quality", "d0_dna", "meta_sizes", "gather", "decode_probe", "decode_tags", "decode_quality", "decode_dna", "decode_assemble"};
+                                     "q0_quality", "d0_dna", "meta_sizes", "gather", "decode_probe", "decode_tags", "decode_quality", "decode_dna", "decode_assemble", "crc32"};
 #define MAX_SLOTS 4
 
 // One in-flight batch of blocks: its own stream, workspace and pinned staging. The scheduler keeps several slots busy so
@@ -111,7 +111,7 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
 {
     if (!out || !dataset || !settings) return DSRCGPU_E_ARG;
     *out = nullptr;
-    if (dataset->color_space || settings->lossy || settings->calc_crc32 || settings->tag_preserve_flags) return DSRCGPU_E_ARG;
+    if (dataset->color_space || settings->lossy || settings->tag_preserve_flags) return DSRCGPU_E_ARG;
     if (dataset->quality_offset < 33 || dataset->quality_offset > 64) return DSRCGPU_E_ARG;
     if (settings->dna_order > 9 || settings->quality_order > 2) return DSRCGPU_E_ARG;
     if (max_block_bytes < 64 || max_block_bytes > (1u << 30)) return DSRCGPU_E_ARG;
@@ -220,6 +220,7 @@ static int status_to_error(dsrcgpu_ctx* ctx, u32 status, u32 blk)
     if (status & 0x100) { code = DSRCGPU_E_CAPACITY; what = "output buffer too small"; }
     else if (status == ST_UNSUPPORTED) { code = DSRCGPU_E_UNSUPPORTED; what = "block outside the supported envelope (see DESIGN.md limits)"; }
     else if (status == ST_OVERFLOW) { code = DSRCGPU_E_UNSUPPORTED; what = "internal stream arena too small for this block"; }
+    else if (status == ST_CRC) { code = DSRCGPU_E_MALFORMED; what = "CRC32 checksums mismatch."; }      // message of src/DsrcWorker.cpp:60
     snprintf(msg, sizeof(msg), "block %u: %s (status %u)", blk, what, status);
     ctx->err = msg;
     return code;
@@ -249,7 +250,7 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     ws.in = d_in; ws.desc = (const BlockDesc*)sl.desc.p; ws.state = (BlockState*)sl.state.p;
     ws.result = (BlockResult*)sl.result.p; ws.probe = (BlockProbe*)sl.probe.p;
     ws.n_blocks = n; ws.qoff = ctx->ds.quality_offset; ws.plus_rep = ctx->ds.plus_repetition;
-    ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order;
+    ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order; ws.calc_crc = ctx->cs.calc_crc32 ? 1u : 0u;
     ws.out = d_out; ws.out_cap = out_cap;
     if (ctx->phase_prof) { if (!ctx->prof.p) { CK(ctx->prof.ensure(64 * 8)); CK(cudaMemsetAsync(ctx->prof.p, 0, 64 * 8, s)); } ws.prof = (u64*)ctx->prof.p; }
 
@@ -307,6 +308,7 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
 
     CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
     { KTimer t(ctx, &sl, K_PARSE); launch_parse(ws, s); }
+    if (ws.calc_crc) { KTimer t(ctx, &sl, K_CRC); launch_crc(ws, s, 0); }
     { KTimer t(ctx, &sl, K_PREP); launch_preprocess(ws, s); }
     { KTimer t(ctx, &sl, K_TAGS); launch_tags(ws, s, ctx->tag_ctas); }
     if (rc_q) { KTimer t(ctx, &sl, K_MODEL_Q); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
@@ -459,7 +461,7 @@ static int decode_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* i
     ws.in = d_in; ws.desc = (const BlockDesc*)sl.desc.p; ws.state = (BlockState*)sl.state.p;
     ws.result = (BlockResult*)sl.result.p; ws.probe = (BlockProbe*)sl.probe.p;
     ws.n_blocks = n; ws.qoff = ctx->ds.quality_offset; ws.plus_rep = ctx->ds.plus_repetition;
-    ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order;
+    ws.dna_order = ctx->cs.dna_order; ws.qua_order = ctx->cs.quality_order; ws.calc_crc = ctx->cs.calc_crc32 ? 1u : 0u;
     ws.out = d_out; ws.out_cap = out_cap;
     CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
     { KTimer t(ctx, &sl, K_DECODE); launch_dec_probe(ws, s); }
@@ -492,6 +494,7 @@ static int decode_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* i
     if (rcd) CK(cudaMemsetAsync(ctx->dec_arena.p, 0, arena_bytes * n, s));
     { KTimer t(ctx, &sl, K_DEC_D); launch_dec_dna(ws, s, sl.ftab.p, pool_nodes, (u8*)ctx->dec_arena.p, arena_bytes, arena_bytes); }
     { KTimer t(ctx, &sl, K_DEC_ASM); launch_dec_assemble(ws, s); }
+    if (ws.calc_crc) { KTimer t(ctx, &sl, K_CRC); launch_crc(ws, s, 1); }
     CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -567,7 +570,7 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
             CK(sl.desc.ensure(sizeof(BlockDesc) * cnt)); CK(sl.state.ensure(sizeof(BlockState) * cnt)); CK(sl.probe.ensure(sizeof(BlockProbe) * cnt));
             for (u32 i = 0; i < cnt; ++i) { memset(&sl.h_desc[i], 0, sizeof(BlockDesc)); sl.h_desc[i].in_off = offs[i]; sl.h_desc[i].in_len = blk_len[first + i]; }
             Workspace pw{};
-            pw.in = d_in; pw.desc = (const BlockDesc*)sl.desc.p; pw.state = (BlockState*)sl.state.p; pw.probe = (BlockProbe*)sl.probe.p; pw.n_blocks = cnt;
+            pw.in = d_in; pw.desc = (const BlockDesc*)sl.desc.p; pw.state = (BlockState*)sl.state.p; pw.probe = (BlockProbe*)sl.probe.p; pw.n_blocks = cnt; pw.calc_crc = ctx->cs.calc_crc32 ? 1u : 0u;
             CK(cudaMemcpyAsync(sl.desc.p, sl.h_desc, sizeof(BlockDesc) * cnt, cudaMemcpyHostToDevice, sl.stream));
             launch_dec_probe(pw, sl.stream);
             CK(cudaMemcpyAsync(sl.h_probe, sl.probe.p, sizeof(BlockProbe) * cnt, cudaMemcpyDeviceToHost, sl.stream));

@@ -20,6 +20,7 @@ enum : u32 {
     ST_MALFORMED = 1,           // invalid / truncated record, line > 65535
     ST_UNSUPPORTED = 2,         // outside the supported envelope (too many fields, symbol >= alphabet, ...)
     ST_OVERFLOW = 3,            // a scratch stream buffer was too small
+    ST_CRC = 5,                 // -c: the decoded block does not match its stored CRC-32 words (4 = decode retry, decode.cu)
 };
 
 // limits of the tag tokenizer (DESIGN.md "limits")
@@ -62,6 +63,7 @@ struct BlockState {
     u8 q_scheme, d_scheme;
     u8 pad[2];
     u32 total_size;
+    u32 crc[3], crc_expected[3];   // -c: CRC-32 of titles / sequences / qualities (computed; read from the block header)
 };
 
 // compact per-block result copied back to the host
@@ -102,6 +104,7 @@ struct Workspace {
     u32 qoff;                   // quality offset
     u32 plus_rep;
     u32 dna_order, qua_order;
+    u32 calc_crc;               // CompressionSettings::calculateCrc32
     u8* tab; u64 tab_stride;    // per-CTA adaptive-row tables of the tile/table model engine (zero between blocks)
     u64* prof;                  // optional: 64 phase cycle counters (clock64 deltas of thread 0 of every CTA), or null
 };

@@ -87,6 +87,7 @@ __global__ void k_dec_probe(Workspace ws)
     BitR r; r.init(ws.in + d.in_off, d.in_len, 0);
     const u32 n = r.be32(), max_len = r.be32(), flags = r.be32(), chunk = r.be32();
     const u32 min_len = (flags & 2u) ? r.be32() : max_len;
+    if (ws.calc_crc) { st.crc_expected[0] = r.be32(); st.crc_expected[1] = r.be32(); st.crc_expected[2] = r.be32(); }   // ReadMetaData :340-355
     st.status = ST_OK;
     if (r.ovr || n == 0 || flags >= 256 || (flags & 1u) || max_len > 65535 || min_len > max_len || chunk >= 0xFFFFFFF0u || n > chunk) st.status = ST_MALFORMED;
     st.n_rec = n; st.max_len = max_len; st.min_len = min_len; st.flags = flags; st.chunk_size = chunk + 1;

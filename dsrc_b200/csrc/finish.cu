@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(DSRC_CTA) k_meta_sizes(Workspace ws, u64 out_b
                 BitW w; w.init(m, d.stream_cap[0]);
                 w.be32(st.n_rec); w.be32(st.max_len); w.be32(st.flags); w.be32(st.chunk_size);
                 if (st.flags & 2u) w.be32(st.min_len);
+                if (ws.calc_crc) { w.be32(st.crc[0]); w.be32(st.crc[1]); w.be32(st.crc[2]); }   // BlockCompressor.cpp:424-440
                 st.stream_size[0] = w.pos;
                 total = st.stream_size[0] + st.stream_size[1] + st.stream_size[2] + st.stream_size[3];
                 st.total_size = total;

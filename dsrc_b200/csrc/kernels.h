@@ -25,3 +25,4 @@ void launch_dec_tags(const Workspace& ws, cudaStream_t s, void* pool, u32 pool_s
 void launch_dec_quality(const Workspace& ws, cudaStream_t s, void* pool, u32 pool_stride, u8* arena, u64 arena_stride, u64 arena_bytes);
 void launch_dec_dna(const Workspace& ws, cudaStream_t s, void* pool, u32 pool_stride, u8* arena, u64 arena_stride, u64 arena_bytes);
 void launch_dec_assemble(const Workspace& ws, cudaStream_t s);
+void launch_crc(const Workspace& ws, cudaStream_t s, u32 decode_mode);   // -c: CRC-32 words of the raw (0) / decoded (1) records

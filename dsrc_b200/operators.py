@@ -28,6 +28,7 @@ class InputParameters:
     qualityCompressionLevel: int = 0      # -q 0..2
     fastqBufferSizeMB: int = 8            # -b 1..1024
     qualityOffset: int = 0                # -o, 0 = auto (src/FastqParser.cpp:27-138)
+    calculateCrc32: bool = False          # -c
     block_bytes: int = 0                  # non-reference extension: chunk buffer in bytes (e.g. 256 KiB); 0 = fastqBufferSizeMB << 20
     max_inflight_blocks: int = 0
 
@@ -145,9 +146,9 @@ def write_header(footer_size, footer_offset, n_blocks):
     return bytes([0xAA, 2, 0, 2]) + struct.pack(">IQQQ", footer_size, footer_offset, 0, n_blocks) + b"\xAA" * 8
 
 
-def write_footer(sizes, quality_offset, plus_rep, dna_order, quality_order):
-    """DsrcFileWriter::WriteFileFooter (src/DsrcFile.cpp:133-170): block sizes are host-endian (LE) u32"""
-    return (b"\xCC" + np.asarray(sizes, dtype="<u4").tobytes() + bytes([1 if plus_rep else 0, quality_offset, 0, dna_order, quality_order])
+def write_footer(sizes, quality_offset, plus_rep, dna_order, quality_order, calc_crc32=False):
+    """DsrcFileWriter::WriteFileFooter (src/DsrcFile.cpp:133-170): block sizes are host-endian (LE) u32; compFlags bit 1 = CRC32"""
+    return (b"\xCC" + np.asarray(sizes, dtype="<u4").tobytes() + bytes([1 if plus_rep else 0, quality_offset, 2 if calc_crc32 else 0, dna_order, quality_order])
             + struct.pack(">Q", 0))
 
 
@@ -161,12 +162,12 @@ def read_archive_index(arc):
     sizes = np.frombuffer(arc[footer_off + 1:footer_off + 1 + 4 * n], dtype="<u4").astype(np.uint32)
     p = footer_off + 1 + 4 * n
     flags, qoff, cflags, dna_order, qua_order = arc[p], arc[p + 1], arc[p + 2], arc[p + 3], arc[p + 4]
-    if flags & 2 or cflags & 3:
-        raise ValueError("colour-space / lossy / CRC archives are outside the supported envelope")
+    if flags & 2 or cflags & 1:
+        raise ValueError("colour-space / lossy archives are outside the supported envelope")
     offs = 40 + np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))[:-1]]).astype(np.uint64)
     if int(offs[-1]) + int(sizes[-1]) > footer_off:
         raise ValueError("Invalid archive footer")
-    return offs, sizes, dict(quality_offset=qoff, plus_repetition=bool(flags & 1), dna_order=dna_order, quality_order=qua_order)
+    return offs, sizes, dict(quality_offset=qoff, plus_repetition=bool(flags & 1), dna_order=dna_order, quality_order=qua_order, calc_crc32=bool(cflags & 2))
 
 
 class DsrcCompressorMT:
@@ -182,7 +183,8 @@ class DsrcCompressorMT:
         if self.encoder is not None:
             return self.encoder(data, offs, lens, caps, settings)
         bc = BlockCompressor(settings["quality_offset"], settings["plus_repetition"], settings["dna_order"], settings["quality_order"],
-                             max_block_bytes=max(int(lens.max()) + 64, 1 << 16), max_inflight_blocks=args.max_inflight_blocks, device=self.device)
+                             max_block_bytes=max(int(lens.max()) + 64, 1 << 16), max_inflight_blocks=args.max_inflight_blocks, device=self.device,
+                             calc_crc32=settings["calc_crc32"])
         try:
             blocks, _, _ = bc.store_many(data, offs, lens, caps=caps)
         finally:
@@ -199,7 +201,7 @@ class DsrcCompressorMT:
         if cs:
             raise ValueError("colour-space FASTQ is outside the supported envelope")
         settings = dict(quality_offset=qoff, plus_repetition=plus_rep, dna_order=args.dnaCompressionLevel * 3,      # DsrcOperator.h:74-90
-                        quality_order=args.qualityCompressionLevel)
+                        quality_order=args.qualityCompressionLevel, calc_crc32=bool(args.calculateCrc32))
         caps = tag_capacities(fastq, offs, lens)
         b0, b1 = shard_ranges(lens, self.world)[self.rank]
         mine = self._encode(fastq, offs[b0:b1], lens[b0:b1], caps[b0:b1], settings, args) if b1 > b0 else []
@@ -211,10 +213,10 @@ class DsrcCompressorMT:
         payload = b"".join(mine)
         archive = None
         if self.world == 1:
-            footer = write_footer(sizes, qoff, plus_rep, settings["dna_order"], settings["quality_order"])
+            footer = write_footer(sizes, qoff, plus_rep, settings["dna_order"], settings["quality_order"], settings["calc_crc32"])
             archive = write_header(len(footer), 40 + len(payload), len(sizes)) + payload + footer
         elif self.rank == 0:
-            footer = write_footer(sizes, qoff, plus_rep, settings["dna_order"], settings["quality_order"])
+            footer = write_footer(sizes, qoff, plus_rep, settings["dna_order"], settings["quality_order"], settings["calc_crc32"])
             total = int(sizes.astype(np.uint64).sum())
             archive = (write_header(len(footer), 40 + total, len(sizes)), footer)      # header + footer; ranks pwrite their slices
         return archive, (my_off, payload)
@@ -229,7 +231,7 @@ class DsrcDecompressorMT:
     def process(self, archive, max_inflight_blocks=0):
         offs, sizes, st = read_archive_index(archive)
         bc = BlockCompressor(st["quality_offset"], st["plus_repetition"], st["dna_order"], st["quality_order"],
-                             max_block_bytes=1 << 20, max_inflight_blocks=max_inflight_blocks, device=self.device)
+                             max_block_bytes=1 << 20, max_inflight_blocks=max_inflight_blocks, device=self.device, calc_crc32=st["calc_crc32"])
         try:
             total = 0
             for o in offs:            # chunkSize + 1 of every block (BlockCompressor.cpp:302-308)

@@ -41,7 +41,7 @@ typedef struct {
     uint32_t quality_order;    /* 0, 1, 2     (= CLI -q, lossless) */
     uint64_t tag_preserve_flags; /* must be 0 (-f field filtering out of scope) */
     uint8_t lossy;             /* must be 0 */
-    uint8_t calc_crc32;        /* must be 0 (-c is a next-tier row) */
+    uint8_t calc_crc32;        /* -c: CRC-32 words of titles / sequences / qualities in every block header (encode), verified on decode */
 } dsrcgpu_settings_t;
 
 enum {

@@ -349,6 +349,8 @@ typedef struct { u32 count; u32 freq[256]; u8 rank[256]; u32 min_len, max_len, r
 
 struct dsrc_oracle {
     u32 qoff; int plus_rep; u32 dna_order, qua_order;
+    int calc_crc;                        /* CompressionSettings::calculateCrc32 (-c) */
+    u32 last_crc[3]; int last_crc_ok;    /* checksums read / verified by the last dsrc_oracle_read */
     u32 tag_cap;                         /* capacity of TagStats::fields (Q1) */
     /* per-block scratch */
     u8* work; u64 work_cap;
@@ -368,6 +370,20 @@ void dsrc_oracle_destroy(dsrc_oracle_t* o)
     free(o->work); free(o->recs); free(o->model); free(o);
 }
 u32 dsrc_oracle_tag_capacity(const dsrc_oracle_t* o) { return o->tag_cap; }
+void dsrc_oracle_set_crc(dsrc_oracle_t* o, int on) { o->calc_crc = on != 0; }
+int dsrc_oracle_last_crc_ok(const dsrc_oracle_t* o) { return o->last_crc_ok; }
+
+/* core::Crc32Hasher (src/Crc32.h:24-92): reflected CRC-32, polynomial 0xEDB88320, seed ~0, final xor ~0 */
+static u32 crc32_update(u32 crc, const u8* p, u32 n)
+{
+    static u32 table[256]; static int ready = 0;
+    if (!ready) {
+        for (u32 i = 0; i < 256; ++i) { u32 h = i; for (int j = 0; j < 8; ++j) h = (h & 1) ? 0xEDB88320u ^ (h >> 1) : h >> 1; table[i] = h; }
+        ready = 1;
+    }
+    for (u32 i = 0; i < n; ++i) crc = (crc >> 8) ^ table[(p[i] ^ crc) & 0xFF];
+    return crc;
+}
 
 static u16* get_model(dsrc_oracle_t* o, u64 entries)
 {
@@ -1071,6 +1087,15 @@ int64_t dsrc_oracle_store(dsrc_oracle_t* o, const u8* fastq, u64 size, u8* out, 
     rc = parse_records(o, size, &n, &chunk_size, raw);
     if (rc < 0) return rc;
     if (n == 0) return ERR_FORMAT;
+    u32 crc[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (o->calc_crc) { /* IRecordsProcessor::ProcessForward(records, n, flags) (RecordsProcessor.cpp:135-152): hash the raw fields first */
+        for (u64 k = 0; k < n; ++k) {
+            const rec_t* r = &o->recs[k];
+            crc[0] = crc32_update(crc[0], o->work + r->title, r->title_len);
+            crc[1] = crc32_update(crc[1], o->work + r->seq, r->seq_len);
+            crc[2] = crc32_update(crc[2], o->work + r->qua, r->qua_len);
+        }
+    }
     preprocess(o, n, &ds, &qs);
     /* AnalyzeMetaData :184-205 */
     if (qs.max_len != qs.min_len) flags |= 2;
@@ -1085,6 +1110,7 @@ int64_t dsrc_oracle_store(dsrc_oracle_t* o, const u8* fastq, u64 size, u8* out, 
     /* StoreMetaData :403-443 */
     bw_u32(&w, (u32)n); bw_u32(&w, qs.max_len); bw_u32(&w, flags); bw_u32(&w, (u32)chunk_size);
     if (flags & 2) bw_u32(&w, qs.min_len);
+    if (o->calc_crc) { bw_u32(&w, ~crc[0]); bw_u32(&w, ~crc[1]); bw_u32(&w, ~crc[2]); }   /* :424-440 */
     bw_flush(&w);
     cmp[0] = w.pos; pos = w.pos;
     /* StoreTags :458-488 */
@@ -1162,6 +1188,8 @@ int64_t dsrc_oracle_read(dsrc_oracle_t* o, const u8* blk, u64 size, u8* out, u64
     br_init(&r, blk, size);
     n = br_u32(&r); max_len = br_u32(&r); flags = br_u32(&r); chunk_size = br_u32(&r);   /* ReadMetaData :300-356 */
     min_len = (flags & 2) ? br_u32(&r) : max_len;
+    o->last_crc_ok = 1;
+    if (o->calc_crc) { o->last_crc[0] = br_u32(&r); o->last_crc[1] = br_u32(&r); o->last_crc[2] = br_u32(&r); }   /* :340-355 */
     br_flush(&r);
     if (r.overrun || n == 0 || flags >= 256 || max_len > 65535 || min_len > max_len) return ERR_FORMAT;
     chunk_size += 1;
@@ -1294,6 +1322,16 @@ tags_done:
             q[i] = (u8)(o->qoff + qv);
         }
     }
+    if (o->calc_crc) { /* BlockCompressor::VerifyChecksum :576-594 */
+        u32 crc[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        for (u32 k = 0; k < n; ++k) {
+            const rec_t* rec = &o->recs[k];
+            crc[0] = crc32_update(crc[0], o->work + rec->title, rec->title_len);
+            crc[1] = crc32_update(crc[1], o->work + rec->seq, rec->qua_len);
+            crc[2] = crc32_update(crc[2], o->work + rec->qua, rec->qua_len);
+        }
+        o->last_crc_ok = (~crc[0] == o->last_crc[0]) && (~crc[1] == o->last_crc[1]) && (~crc[2] == o->last_crc[2]);
+    }
     memcpy(out, o->work, chunk_size);
     return (int64_t)chunk_size;
 }
@@ -1371,6 +1409,7 @@ static void put_be64(u8* p, u64 v) { put_be32(p, (u32)(v >> 32)); put_be32(p + 4
 static u32 get_be32(const u8* p) { return ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | p[3]; }
 static u64 get_be64(const u8* p) { return ((u64)get_be32(p) << 32) | get_be32(p + 4); }
 
+static int g_archive_crc = 0;   /* set by dsrc_oracle_compress_mem_crc around its call */
 int64_t dsrc_oracle_write_archive(const u8* blocks, const u32* sizes, u64 nb, u32 qoff, int plus_rep, int color_space,
                                   u32 dna_order, u32 qua_order, u8* out, u64 cap)
 {
@@ -1388,7 +1427,7 @@ int64_t dsrc_oracle_write_archive(const u8* blocks, const u32* sizes, u64 nb, u3
     for (u64 i = 0; i < nb; ++i) { u32 v = sizes[i]; out[p++] = (u8)v; out[p++] = (u8)(v >> 8); out[p++] = (u8)(v >> 16); out[p++] = (u8)(v >> 24); } /* host-endian (LE) */
     out[p++] = (u8)((plus_rep ? 1 : 0) | (color_space ? 2 : 0));
     out[p++] = (u8)qoff;
-    out[p++] = 0;                /* lossy / crc flags */
+    out[p++] = (u8)(g_archive_crc ? 2 : 0);   /* compFlags: bit0 lossy, bit1 crc (DsrcFile.cpp:155-165) */
     out[p++] = (u8)dna_order; out[p++] = (u8)qua_order;
     put_be64(out + p, 0); p += 8; /* tagPreserveFlags */
     return (int64_t)p;
@@ -1402,6 +1441,7 @@ int64_t dsrc_oracle_compress_mem(const u8* file, u64 size, u32 dna_level, u32 qu
     dsrc_oracle_cut_blocks(file, size, buf_bytes, off, len, nb);
     if (nb == 0 || !dsrc_oracle_analyze(file + off[0], len[0], &qoff, &plus_rep, &cs) || cs) { res = ERR_FORMAT; goto done; }
     o = dsrc_oracle_create(qoff, plus_rep, dna_level * 3, qua_level); /* DsrcOperator.h:74-90 */
+    o->calc_crc = g_archive_crc;
     for (u64 b = 0; b < nb; ++b) {
         int64_t s = dsrc_oracle_store(o, file + off[b], len[b], tmp + total, size + size / 2 + 4096 - total, NULL, NULL);
         if (s < 0) { res = s; break; }
@@ -1412,6 +1452,15 @@ int64_t dsrc_oracle_compress_mem(const u8* file, u64 size, u32 dna_level, u32 qu
 done:
     free(off); free(len); free(sizes); free(tmp);
     return res;
+}
+
+int64_t dsrc_oracle_compress_mem_crc(const u8* file, u64 size, u32 dna_level, u32 qua_level, u64 buf_bytes, u32 qoff, int crc, u8* out, u64 cap)
+{
+    int64_t r;
+    g_archive_crc = crc != 0;
+    r = dsrc_oracle_compress_mem(file, size, dna_level, qua_level, buf_bytes, qoff, out, cap);
+    g_archive_crc = 0;
+    return r;
 }
 
 int64_t dsrc_oracle_decompress_mem(const u8* arc, u64 size, u8* out, u64 cap)
@@ -1425,9 +1474,10 @@ int64_t dsrc_oracle_decompress_mem(const u8* arc, u64 size, u8* out, u64 cap)
     if (f[0] != 0xCC) return ERR_FORMAT;
     p = 1 + nb * 4;
     plus_rep = f[p] & 1; if (f[p] & 2) return ERR_UNSUPPORTED; qoff = f[p + 1];
-    if (f[p + 2] & 3) return ERR_UNSUPPORTED;
+    if (f[p + 2] & 1) return ERR_UNSUPPORTED;
     dna_order = f[p + 3]; qua_order = f[p + 4];
     o = dsrc_oracle_create(qoff, plus_rep, dna_order, qua_order);
+    o->calc_crc = (f[p + 2] & 2) != 0;
     p = 40;
     for (u64 b = 0; b < nb; ++b) {
         u32 bs = (u32)f[1 + b * 4] | ((u32)f[2 + b * 4] << 8) | ((u32)f[3 + b * 4] << 16) | ((u32)f[4 + b * 4] << 24);
@@ -1435,6 +1485,7 @@ int64_t dsrc_oracle_decompress_mem(const u8* arc, u64 size, u8* out, u64 cap)
         if (p + bs > foot_off) { res = ERR_FORMAT; break; }
         s = dsrc_oracle_read(o, arc + p, bs, out + total, cap - total);
         if (s < 0) { res = s; break; }
+        if (!o->last_crc_ok) { res = ERR_FORMAT; break; }
         total += (u64)s; p += bs;
     }
     dsrc_oracle_destroy(o);

@@ -40,6 +40,12 @@ int64_t dsrc_oracle_store(dsrc_oracle_t* o, const uint8_t* fastq, uint64_t size,
 int64_t dsrc_oracle_read(dsrc_oracle_t* o, const uint8_t* blk, uint64_t size,
                          uint8_t* out, uint64_t cap);
 
+/* CompressionSettings::calculateCrc32 (CLI -c): Store adds the three CRC-32 words (titles, sequences, qualities of the
+ * raw records, src/RecordsProcessor.cpp:135-152) to the block header (BlockCompressor.cpp:424-440); Read parses them and
+ * dsrc_oracle_last_crc_ok tells whether the decoded block matched (VerifyChecksum, :576-594). */
+void dsrc_oracle_set_crc(dsrc_oracle_t* o, int on);
+int dsrc_oracle_last_crc_ok(const dsrc_oracle_t* o);
+
 /* Current emulated capacity of TagStats::fields (for tests of Q1). */
 uint32_t dsrc_oracle_tag_capacity(const dsrc_oracle_t* o);
 
@@ -64,6 +70,9 @@ int64_t dsrc_oracle_write_archive(const uint8_t* blocks, const uint32_t* block_s
  * dna_level/quality_level as on the CLI (-d/-q); buf_bytes = chunk buffer size (CLI: MB<<20). */
 int64_t dsrc_oracle_compress_mem(const uint8_t* file, uint64_t size, uint32_t dna_level, uint32_t quality_level,
                                  uint64_t buf_bytes, uint32_t quality_offset, uint8_t* out, uint64_t cap);
+
+int64_t dsrc_oracle_compress_mem_crc(const uint8_t* file, uint64_t size, uint32_t dna_level, uint32_t quality_level,
+                                     uint64_t buf_bytes, uint32_t quality_offset, int crc, uint8_t* out, uint64_t cap);
 
 /* Whole-archive decompress == DsrcDecompressorST::Process (src/DsrcOperator.cpp:165) on memory. */
 int64_t dsrc_oracle_decompress_mem(const uint8_t* arc, uint64_t size, uint8_t* out, uint64_t cap);

@@ -108,6 +108,24 @@ int ref_compress_file(const char* in_, const char* out_, int dnaLevel, int quaLe
 	return ok ? 0 : -1;
 }
 
+int ref_compress_file_crc(const char* in_, const char* out_, int dnaLevel, int quaLevel, int bufMB, int threads, unsigned qoff, int crc)
+{
+	comp::InputParameters p;
+	p.inputFilename = in_;
+	p.outputFilename = out_;
+	p.dnaCompressionLevel = dnaLevel;
+	p.qualityCompressionLevel = quaLevel;
+	p.fastqBufferSizeMB = bufMB;
+	p.threadNum = threads;
+	p.qualityOffset = qoff;
+	p.calculateCrc32 = crc != 0;
+	comp::IDsrcOperator* op = (threads == 1) ? (comp::IDsrcOperator*)new comp::DsrcCompressorST()
+											 : (comp::IDsrcOperator*)new comp::DsrcCompressorMT();
+	bool ok = op->Process(p);
+	delete op;
+	return ok ? 0 : -1;
+}
+
 int ref_decompress_file(const char* in_, const char* out_, int threads)
 {
 	comp::InputParameters p;

@@ -52,6 +52,11 @@ def main():
             arc = open(dst, "rb").read()
             out["archives"]["illumina8000_seed7_d%d_q%d_b1" % (dl, ql)] = {
                 "dna_level": dl, "quality_level": ql, "buf_mb": 1, "input_sha256": sha(big), "archive_sha256": sha(arc), "archive_bytes": len(arc)}
+        dst = os.path.join(tmp, "c.dsrc")        # -c: CRC-32 words in every block header, crc flag in the footer
+        assert R.compress_file(src, dst, 2, 2, 1, 1, 0, crc=True) == 0
+        arc = open(dst, "rb").read()
+        out["archives"]["illumina8000_seed7_d2_q2_b1_crc"] = {"dna_level": 2, "quality_level": 2, "buf_mb": 1, "crc": True, "input_sha256": sha(big),
+                                                             "archive_sha256": sha(arc), "archive_bytes": len(arc)}
     json.dump(out, open(os.path.join(HERE, "blocks.json"), "w"), indent=1, sort_keys=True)
     print("wrote", len(out["cases"]), "cases,", len(out["archives"]), "archives")
 

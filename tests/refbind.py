@@ -13,7 +13,7 @@ def _buf(b):
 
 
 class Oracle:
-    def __init__(self, qoff=33, plus_rep=0, dna_order=0, qua_order=0):
+    def __init__(self, qoff=33, plus_rep=0, dna_order=0, qua_order=0, crc=False):
         self.lib = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
         L = self.lib
         L.dsrc_oracle_create.restype = C.c_void_p
@@ -31,7 +31,17 @@ class Oracle:
         L.dsrc_oracle_decompress_mem.argtypes = [C.c_char_p, C.c_uint64, _u8p, C.c_uint64]
         L.dsrc_oracle_analyze.restype = C.c_int
         L.dsrc_oracle_analyze.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.dsrc_oracle_set_crc.argtypes = [C.c_void_p, C.c_int]
+        L.dsrc_oracle_last_crc_ok.restype = C.c_int
+        L.dsrc_oracle_last_crc_ok.argtypes = [C.c_void_p]
+        L.dsrc_oracle_compress_mem_crc.restype = C.c_int64
+        L.dsrc_oracle_compress_mem_crc.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, _u8p, C.c_uint64]
         self.h = L.dsrc_oracle_create(qoff, plus_rep, dna_order, qua_order)
+        if crc:
+            L.dsrc_oracle_set_crc(self.h, 1)
+
+    def crc_ok(self):
+        return bool(self.lib.dsrc_oracle_last_crc_ok(self.h))
 
     def __del__(self):
         try:
@@ -71,10 +81,10 @@ class Oracle:
         self.lib.dsrc_oracle_cut_blocks(data, len(data), cbuf, off, ln, n)
         return [(off[i], ln[i]) for i in range(n)]
 
-    def compress(self, data, d, q, buf_bytes, qoff=0):
+    def compress(self, data, d, q, buf_bytes, qoff=0, crc=False):
         cap = len(data) * 2 + (1 << 16)
         out = (C.c_uint8 * cap)()
-        n = self.lib.dsrc_oracle_compress_mem(data, len(data), d, q, buf_bytes, qoff, out, cap)
+        n = self.lib.dsrc_oracle_compress_mem_crc(data, len(data), d, q, buf_bytes, qoff, int(crc), out, cap)
         if n < 0:
             raise RuntimeError("oracle compress failed: %d" % n)
         return bytes(out[:n])
@@ -94,7 +104,7 @@ def ref_available():
 class Ref:
     """the unmodified reference's BlockCompressor (one instance == one worker's compressor)."""
 
-    def __init__(self, qoff=33, plus_rep=0, dna_order=0, qua_order=0):
+    def __init__(self, qoff=33, plus_rep=0, dna_order=0, qua_order=0, crc=False):
         self.lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libdsrcref.so"))
         L = self.lib
         L.ref_bc_create.restype = C.c_void_p
@@ -106,7 +116,8 @@ class Ref:
         L.ref_bc_read.argtypes = [C.c_void_p, C.c_char_p, C.c_ulonglong, _u8p, C.c_ulonglong]
         L.ref_compress_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
         L.ref_decompress_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
-        self.h = L.ref_bc_create(qoff, plus_rep, 0, dna_order, qua_order, 0, 0)
+        L.ref_compress_file_crc.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int]
+        self.h = L.ref_bc_create(qoff, plus_rep, 0, dna_order, qua_order, 0, int(crc))
 
     def __del__(self):
         try:
@@ -132,8 +143,8 @@ class Ref:
             raise RuntimeError("ref read failed")
         return bytes(out[:n])
 
-    def compress_file(self, src, dst, d, q, buf_mb, threads=1, qoff=0):
-        return self.lib.ref_compress_file(src.encode(), dst.encode(), d, q, buf_mb, threads, qoff)
+    def compress_file(self, src, dst, d, q, buf_mb, threads=1, qoff=0, crc=False):
+        return self.lib.ref_compress_file_crc(src.encode(), dst.encode(), d, q, buf_mb, threads, qoff, int(crc))
 
     def decompress_file(self, src, dst, threads=1):
         return self.lib.ref_decompress_file(src.encode(), dst.encode(), threads)

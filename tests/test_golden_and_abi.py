@@ -41,7 +41,7 @@ def test_oracle_matches_golden_archives(name):
     g = GOLD["archives"][name]
     big = synth.illumina(8000, seed=7)
     assert sha(big) == g["input_sha256"]
-    arc = refbind.Oracle().compress(big, g["dna_level"], g["quality_level"], g["buf_mb"] << 20, 0)
+    arc = refbind.Oracle().compress(big, g["dna_level"], g["quality_level"], g["buf_mb"] << 20, 0, crc=g.get("crc", False))
     assert sha(arc) == g["archive_sha256"]
     assert refbind.Oracle().decompress(arc, len(big) + 64) == big
 

@@ -44,3 +44,12 @@ def test_decompress_reference_archive_454():
     data = synth.ion454(400, seed=8)
     arc = refbind.Oracle().compress(data, 3, 2, 1 << 20, 0)
     assert DsrcDecompressorMT().process(arc) == data
+
+
+def test_archive_with_crc32_matches_reference():
+    from dsrc_b200 import DsrcCompressorMT, DsrcDecompressorMT, InputParameters
+    big = synth.illumina(8000, seed=7)
+    arc, _ = DsrcCompressorMT().process(InputParameters(2, 2, 1, 0, calculateCrc32=True), big)
+    assert arc == refbind.Oracle().compress(big, 2, 2, 1 << 20, 0, crc=True)
+    assert hashlib.sha256(arc).hexdigest() == GOLD["archives"]["illumina8000_seed7_d2_q2_b1_crc"]["archive_sha256"]
+    assert DsrcDecompressorMT().process(arc) == big

@@ -76,3 +76,17 @@ def test_bench_shape_roundtrip_sha():
     dec = bc.read_many(arc, offs, [len(e) for e in enc], out_cap=len(big) + 64)
     assert hashlib.sha256(b"".join(dec)).digest() == hashlib.sha256(big).digest()
     bc.close()
+
+
+def test_crc32_mismatch_is_reported():
+    """decode with -c verifies the stored CRC-32 words like BlockCompressor::VerifyChecksum (src/BlockCompressor.cpp:576-594)"""
+    from dsrc_b200 import BlockCompressor, DsrcGpuError
+    data = synth.illumina(400, seed=61, regime="full")
+    blk, _, _ = refbind.Oracle(33, 0, 6, 2, crc=True).store(data[:-1])
+    bc = BlockCompressor(33, False, 6, 2, max_block_bytes=1 << 18, calc_crc32=True)
+    assert bc.read(blk, out_cap=len(data) + 64) == data
+    bad = bytearray(blk)
+    bad[17] ^= 0xFF                        # inside the stored title CRC word
+    with pytest.raises(DsrcGpuError, match="CRC32"):
+        bc.read(bytes(bad), out_cap=len(data) + 64)
+    bc.close()

@@ -134,3 +134,20 @@ def test_bench_shape_blocks_match_oracle():
         for i, (o, l) in enumerate(blocks):
             assert got[i] == ora.store(big[o:o + l])[0], (profile, i)
         bc.close()
+
+
+@pytest.mark.parametrize("d,q", [(6, 2), (0, 0), (9, 1)])
+def test_crc32_blocks_match_oracle(d, q):
+    """-c: CRC-32 words of titles / sequences / qualities in the block header"""
+    from dsrc_b200 import BlockCompressor
+    for data in (synth.illumina(900, seed=51, regime="full"), synth.ion454(200, seed=52, iupac=(d != 0)), synth.illumina(3, seed=53)):
+        chunk = data[:-1]
+        ora = refbind.Oracle(33, 0, d, q, crc=True)
+        bc = BlockCompressor(33, False, d, q, max_block_bytes=max(len(chunk) + 64, 1 << 16), calc_crc32=True)
+        for it in range(2):
+            exp, _, ecmp = ora.store(chunk)
+            got, _, gcmp = bc.store(chunk)
+            assert gcmp == ecmp
+            assert got == exp
+        assert bc.read(got, out_cap=len(data) + 64) == data
+        bc.close()

@@ -17,7 +17,7 @@ def _oracle_encoder(data, offs, lens, caps, st):
     """test stand-in for the device call: one oracle instance per block, its field-vector capacity forced through a warm-up title"""
     out = []
     for o, l, c in zip(offs, lens, caps):
-        ora = refbind.Oracle(st["quality_offset"], int(st["plus_repetition"]), st["dna_order"], st["quality_order"])
+        ora = refbind.Oracle(st["quality_offset"], int(st["plus_repetition"]), st["dna_order"], st["quality_order"], crc=st.get("calc_crc32", False))
         chunk = bytes(memoryview(data)[int(o):int(o) + int(l)])
         if c:        # bring TagStats::fields to capacity c: a block whose first title has c fields (2 records so Analyze-free Store works)
             title = b"@" + b" ".join([b"x"] * int(c))
@@ -50,12 +50,17 @@ def test_header_footer_match_oracle_archive():
     big = synth.illumina(8000, seed=7)
     arc = refbind.Oracle().compress(big, 2, 2, 1 << 20, 0)
     offs, sizes, st = op.read_archive_index(arc)
-    assert st == dict(quality_offset=33, plus_repetition=False, dna_order=6, quality_order=2)
+    assert st == dict(quality_offset=33, plus_repetition=False, dna_order=6, quality_order=2, calc_crc32=False)
     footer = op.write_footer(sizes, 33, False, 6, 2)
     total = int(sizes.astype(np.uint64).sum())
     assert op.write_header(len(footer), 40 + total, len(sizes)) == arc[:40]
     assert footer == arc[40 + total:]
     assert int(offs[0]) == 40
+    arc_c = refbind.Oracle().compress(big, 2, 2, 1 << 20, 0, crc=True)
+    offs, sizes, st = op.read_archive_index(arc_c)
+    assert st["calc_crc32"] is True
+    total = int(sizes.astype(np.uint64).sum())
+    assert op.write_footer(sizes, 33, False, 6, 2, True) == arc_c[40 + total:]
 
 
 def test_shard_ranges_cover_and_balance():

@@ -62,3 +62,33 @@ def test_whole_file_matches_reference_cli_path(tmp_path):
         orc = refbind.Oracle().compress(big, dl, ql, 1 << 20, 0)
         assert ref == orc
         assert refbind.Oracle().decompress(ref, len(big) + 64) == big
+
+
+def test_crc32_blocks_and_archive_match_reference(tmp_path):
+    """-c: three CRC-32 words in the block header, crc flag in the footer; verify-by-decode"""
+    import synth
+    for data, d, q in [(synth.illumina(500, seed=31), 6, 2), (synth.ion454(150, seed=32), 9, 2), (synth.illumina(300, seed=33, regime="full"), 0, 0)]:
+        chunk = data[:-1]
+        o = refbind.Oracle(33, 0, d, q, crc=True)
+        r = refbind.Ref(33, 0, d, q, crc=True)
+        for it in range(2):
+            a, _, ca = o.store(chunk)
+            b, _, cb = r.store(chunk)
+            assert a == b and ca == cb
+        assert o.read(a) == data and o.crc_ok()
+        assert r.read(a) == data
+        bad = bytearray(a)
+        bad[len(bad) * 2 // 3] ^= 0x10
+        try:
+            o.read(bytes(bad))
+            assert not o.crc_ok()
+        except RuntimeError:
+            pass
+    big = synth.illumina(8000, seed=7)
+    src = tmp_path / "in.fq"
+    src.write_bytes(big)
+    dst = tmp_path / "c.dsrc"
+    assert refbind.Ref().compress_file(str(src), str(dst), 2, 2, 1, 1, 0, crc=True) == 0
+    arc = dst.read_bytes()
+    assert arc == refbind.Oracle().compress(big, 2, 2, 1 << 20, 0, crc=True)
+    assert refbind.Oracle().decompress(arc, len(big) + 64) == big
