@@ -523,13 +523,15 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
     if (const char* e = getenv("DSRCGPU_DEC_ARENA_KB")) tier0 = std::max<u64>(64, (u64)atoll(e)) << 10;
     const u64 tiers[3] = {tier0, std::max<u64>(tier0, 8ull << 20), std::max<u64>(big, 8ull << 20)};
     const u32 pools[3] = {8192u, 65536u, 262144u};        // Huffman nodes (8 B) per block
-    const u64 small = tiers[0], budget = 16ull << 30;
+    const u64 budget = 24ull << 30;
+    int start_tier = 0;                                   // raised when most blocks of a batch had to retry (large-alphabet data)
     u32 dec_batch = 32768;
     if (const char* e = getenv("DSRCGPU_DEC_BATCH")) dec_batch = (u32)std::max(1, atoi(e));
-    const u32 per_batch = (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / small));
+    const u32 per_batch0 = (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / tiers[0]));
     std::vector<u32> idx, status, sizes, retry; std::vector<u64> offs, ooffs;
     u64 out_pos = 0;
-    for (u32 first = 0; first < n; first += per_batch) {
+    for (u32 first = 0; first < n;) {
+        const u32 per_batch = start_tier == 0 ? per_batch0 : (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / (tiers[start_tier] + (u64)pools[start_tier] * 8)));
         const u32 cnt = std::min(per_batch, n - first);
         idx.resize(cnt); offs.resize(cnt); ooffs.resize(cnt); status.resize(cnt); sizes.resize(cnt);
         for (u32 i = 0; i < cnt; ++i) idx[i] = first + i;
@@ -577,14 +579,15 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
             CK(cudaStreamSynchronize(sl.stream));
             for (u32 i = 0; i < cnt; ++i) { ooffs[i] = out_pos + batch_bytes; batch_bytes += sl.h_probe[i].n_fields ? sl.h_probe[i].n_fields : 1; }
         }
-        int rc = decode_batch(ctx, sl, d_in, idx.data(), offs.data(), blk_len, ooffs.data(), cnt, d_out, cap, small, pools[0], status.data(), sizes.data());
+        int rc = decode_batch(ctx, sl, d_in, idx.data(), offs.data(), blk_len, ooffs.data(), cnt, d_out, cap, tiers[start_tier], pools[start_tier], status.data(), sizes.data());
         if (rc) return rc;
         retry.clear();
         for (u32 i = 0; i < cnt; ++i) {
             if (status[i] == DEC_ST_RETRY) { retry.push_back(i); continue; }
             if (status[i] != ST_OK) { int e = status_to_error(ctx, status[i], first + i); if (e == DSRCGPU_E_MALFORMED) ctx->err += " (corrupt compressed block)"; return e; }
         }
-        for (int tier = 1; tier < 3 && !retry.empty(); ++tier) {
+        const size_t n_retry0 = retry.size();
+        for (int tier = start_tier + 1; tier < 3 && !retry.empty(); ++tier) {
             const u32 group = (u32)std::max<u64>(1, budget / (tiers[tier] + (u64)pools[tier] * 8));
             std::vector<u32> again;
             for (size_t g0 = 0; g0 < retry.size(); g0 += group) {
@@ -606,6 +609,8 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
             CK(cudaStreamSynchronize(sl.stream));
         }
         out_pos += batch_bytes;
+        if (start_tier < 1 && n_retry0 * 2 > cnt) start_tier = 1;
+        first += cnt;
     }
     cudaEventRecord(ctx->call_b, sl.stream);
     CK(cudaEventSynchronize(ctx->call_b));

@@ -355,20 +355,61 @@ __device__ __forceinline__ u32 rc_decode_row(RcDec& rc, u16* p, bool fresh)
     } else p[idx] = (u16)(f + 2);
     return idx;
 }
-__device__ u32 rc_decode_row_mem(RcDec& rc, u16* stt, u32 N, bool fresh)
+// rows of 32 / 64 / 128 counters stay in memory (L1): one pass of 16-byte loads gives the sums of the groups of 8 counters (kept in
+// registers) and the total; the group holding the cumulative target is reloaded and searched.
+__device__ __forceinline__ u32 hsum8(const uint4 v)
 {
-    if (fresh) for (u32 i = 0; i < N; ++i) stt[i] = 1;
+    const u32 a = (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16);
+    return a + (v.z & 0xFFFFu) + (v.z >> 16) + (v.w & 0xFFFFu) + (v.w >> 16);
+}
+template <int N>
+__device__ u32 rc_decode_row_big(RcDec& rc, u16* stt, bool fresh)
+{
+    uint4* row = (uint4*)stt;
+    u32 g[N / 8];
     u32 tot = 0;
-    for (u32 i = 0; i < N; i += 8) {
-        const uint4 v = *(const uint4*)(stt + i);
-        tot += (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) + (v.w & 0xFFFFu) + (v.w >> 16);
+    if (fresh) {
+        const uint4 ones = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u);
+#pragma unroll
+        for (int k = 0; k < N / 8; ++k) { row[k] = ones; g[k] = 8; }
+        tot = N;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N / 8; ++k) { g[k] = hsum8(row[k]); tot += g[k]; }
     }
-    if (tot >= (1u << 16) - 2 * N) { tot = 0; for (u32 i = 0; i < N; ++i) { const u32 c = stt[i] - (stt[i] >> 1); stt[i] = (u16)c; tot += c; } }
+    if (tot >= (1u << 16) - 2 * N) {
+        tot = 0;
+#pragma unroll
+        for (int k = 0; k < N / 8; ++k) {
+            uint4 v = row[k];
+            u32* w = (u32*)&v;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { u32 lo = w[j] & 0xFFFFu, hi = w[j] >> 16; lo -= lo >> 1; hi -= hi >> 1; w[j] = lo | (hi << 16); }
+            row[k] = v; g[k] = hsum8(v); tot += g[k];
+        }
+    }
     const u32 cul = rc.cum(tot);
-    u32 idx = 0, hi = 0;
-    for (;; ++idx) { hi += stt[idx]; if (hi > cul || idx + 1 >= N) break; }
-    const u32 f = stt[idx];
-    rc.update(f, hi - f);
+    u32 gi = N / 8 - 1, before = 0, acc = 0; bool found = false;
+#pragma unroll
+    for (int k = 0; k < N / 8; ++k) {
+        const bool hit = !found && (acc + g[k] > cul || k == N / 8 - 1);
+        if (hit) { gi = k; before = acc; found = true; }
+        acc += g[k];
+    }
+    const uint4 v = row[gi];
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
+    u32 j = 7, f = 0, hi = 0; acc = before; found = false;
+    const bool last_group = gi == N / 8 - 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const u32 c = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+        acc += c;
+        const bool hit = !found && (acc > cul || (k == 7 && last_group));
+        if (hit) { j = k; f = c; hi = acc - c; found = true; }
+    }
+    if (!found) { j = 7; f = (w[3] >> 16) & 0xFFFFu; hi = acc - f; }     // cannot happen for a consistent row; keeps the state defined
+    rc.update(f, hi);
+    const u32 idx = gi * 8 + j;
     stt[idx] = (u16)(f + 2);
     return idx;
 }
@@ -378,7 +419,9 @@ __device__ __forceinline__ u32 rc_decode_any(RcDec& rc, u16* p, u32 N, bool fres
     case 4: return rc_decode_row<4>(rc, p, fresh);
     case 8: return rc_decode_row<8>(rc, p, fresh);
     case 16: return rc_decode_row<16>(rc, p, fresh);
-    default: return rc_decode_row_mem(rc, p, N, fresh);
+    case 32: return rc_decode_row_big<32>(rc, p, fresh);
+    case 64: return rc_decode_row_big<64>(rc, p, fresh);
+    default: return rc_decode_row_big<128>(rc, p, fresh);
     }
 }
 
