@@ -63,6 +63,7 @@ __device__ void dna_cfg(u32 order, u32 scheme, ModelCfg& c)
 #define TRIP(f, cum, tot) ((u64)(f) | ((u64)(cum) << 16) | ((u64)(tot) << 32))
 #define PROF_MARK(slot) do { if (ws.prof && threadIdx.x == 0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&ws.prof[slot], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
 #include "model_tab.cuh"
+#include "model_dna.cuh"
 
 struct ModelShared {
     union {
@@ -72,6 +73,7 @@ struct ModelShared {
             struct { u32 B[DSRC_WARPS][128]; u32 P[DSRC_WARPS][128]; } l;                        // long-run walker: per-warp row state
         } g;
         TabShared tab;                             // tile/table engine (model_tab.cuh)
+        DnaDirectShared dna;                       // shared-memory table engine of the 4-symbol DNA model (model_dna.cuh)
     } u;
     u32 scan[DSRC_WARPS + 1];
     u32 n_long, n_heads;
@@ -352,7 +354,8 @@ __device__ void group_scan(ModelShared& S, const u64* sorted, u32* longq, u64* t
 template <bool QUALITY>
 __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_stride)
 {
-    __shared__ ModelShared S;
+    extern __shared__ __align__(16) u8 model_smem[];       // sizeof(ModelShared) > 48 KiB: opt-in dynamic shared memory
+    ModelShared& S = *(ModelShared*)model_smem;
     TabShared& TS = S.u.tab;
     const u32 tid = threadIdx.x;
     u64* bufA = ws.elem_a + (u64)blockIdx.x * arena_stride;
@@ -411,6 +414,12 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
                 for (u32 j = lane_id(); j < len; j += 32) pc[qo + j] = (u8)(j * cfg.rescale / len);
             }
             __syncthreads();
+        }
+        if (!QUALITY && cfg.alpha == 4 && cfg.key_bits <= 12) {
+            // ---- whole table in shared memory (model_dna.cuh)
+            dna_direct_engine(S.u.dna, ws.dcat + d.sym_base, M, cfg.ord, trip);
+            PROF_MARK(prof_base + 6);
+            continue;
         }
         if (tabpath) {
             // ---- tile/table engine (model_tab.cuh)
@@ -527,8 +536,13 @@ static u32 model_grid(const Workspace& ws, u32 max_ctas)
     if (g > ws.n_blocks) g = ws.n_blocks;
     return g ? g : 1;
 }
-void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { k_model<true><<<model_grid(ws, ctas), DSRC_CTA, 0, s>>>(ws, stride); }
-void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { k_model<false><<<model_grid(ws, ctas), DSRC_CTA, 0, s>>>(ws, stride); }
+static void model_smem_optin()
+{
+    cudaFuncSetAttribute(k_model<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
+    cudaFuncSetAttribute(k_model<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
+}
+void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<true><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
+void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
 void launch_rc_encode(const Workspace& ws, cudaStream_t s)
 {
     const u32 dq = ws.qua_order > 0, dd = ws.dna_order > 0;
