@@ -33,7 +33,7 @@ struct DevBuf {
 enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_DEC_TAGS, K_DEC_Q, K_DEC_D, K_DEC_ASM, K_CRC, K_NUM };
 static const char* K_NAMES[K_NUM] = {"count_lines", "parse", "preprocess", "tags", "model_quality", "model_dna", "rc_encode",
                                      "q0_quality", "d0_dna", "meta_sizes", "gather", "decode_probe", "decode_tags", "decode_quality", "decode_dna", "decode_assemble", "crc32"};
-#define MAX_SLOTS 4
+#define MAX_SLOTS 8
 
 // One in-flight batch of blocks: its own stream, workspace and pinned staging. The scheduler keeps several slots busy so
 // that the copies of one batch, the parallel kernels of the next and the serial range-coder chains of a third overlap.
@@ -96,8 +96,15 @@ struct KTimer {
 };
 static void collect_times(dsrcgpu_ctx* ctx, Slot* sl)
 {
+    static FILE* tl = nullptr;                        // developer aid: DSRCGPU_TIMELINE=<file> dumps every kernel's start/end on its stream
+    static bool tl_checked = false;
+    if (!tl_checked) { tl_checked = true; if (const char* e = getenv("DSRCGPU_TIMELINE")) tl = fopen(e, "w"); }
     for (auto& u : sl->ev_used) {
         float ms = 0; cudaEventElapsedTime(&ms, u.second.first, u.second.second);
+        if (tl && ctx->call_a) {
+            float t0 = 0; cudaEventElapsedTime(&t0, ctx->call_a, u.second.first);
+            fprintf(tl, "%d,%s,%.3f,%.3f\n", (int)(sl - ctx->slots), K_NAMES[u.first], t0, t0 + ms); fflush(tl);
+        }
         ctx->k_ms[u.first] += ms;
         ctx->ev_pool.push_back(u.second.first); ctx->ev_pool.push_back(u.second.second);
     }
@@ -144,7 +151,11 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     // before), fewer if the sort arenas (2 x 8 B x block/2 entries each) would exceed ~8 GiB per slot
     ctx->model_stride = (u64)max_block_bytes / 2 + 64;
     u64 per_cta = ctx->model_stride * 8 * 2;
-    u64 ctas = std::min<u64>((u64)ctx->sms * (ctx->n_slots > 1 ? 3 : 4), std::max<u64>(1, (8ull << 30) / per_cta));
+    // several slots run their persistent kernels side by side, so each slot gets its share of the 4 CTA slots per SM
+    u64 want = (u64)ctx->sms * 4;
+    if (ctx->n_slots > 1) want = std::max<u64>(ctx->sms, (u64)ctx->sms * 4 * 3 / (2 * ctx->n_slots));
+    if (const char* e = getenv("DSRCGPU_MODEL_CTAS")) want = (u64)std::max(1, atoi(e));
+    u64 ctas = std::min<u64>(want, std::max<u64>(1, (8ull << 30) / per_cta));
     ctas = std::min<u64>(ctas, max_inflight_blocks);
     ctx->model_ctas = (u32)ctas;
     {   // adaptive-row tables of the tile/table model engine: rows of 2N bytes, one table per persistent CTA
