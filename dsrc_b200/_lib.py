@@ -57,6 +57,16 @@ def lib():
     L.dsrcgpu_set_profiling.argtypes = [vp, C.c_int]
     L.dsrcgpu_phase_cycles.restype = C.c_int
     L.dsrcgpu_phase_cycles.argtypes = [vp, u64p, C.c_int]
+    L.dsrcgpu_analyze_first_chunk.restype = C.c_int
+    L.dsrcgpu_analyze_first_chunk.argtypes = [vp, C.c_uint64, C.POINTER(Dataset)]
+    L.dsrcgpu_archive_footer_size.restype = C.c_uint64
+    L.dsrcgpu_archive_footer_size.argtypes = [C.c_uint64]
+    L.dsrcgpu_write_archive_header.restype = C.c_int
+    L.dsrcgpu_write_archive_header.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.dsrcgpu_write_archive_footer.restype = C.c_int
+    L.dsrcgpu_write_archive_footer.argtypes = [vp, C.c_uint64, u32p, C.c_uint64, C.POINTER(Dataset), C.POINTER(Settings)]
+    L.dsrcgpu_read_archive_index.restype = C.c_int
+    L.dsrcgpu_read_archive_index.argtypes = [vp, C.c_uint64, u64p, u64p, u32p, C.c_uint64, C.POINTER(Dataset), C.POINTER(Settings)]
     L.dsrcgpu_release_workspace.restype = C.c_int
     L.dsrcgpu_release_workspace.argtypes = [vp]
     L.dsrcgpu_device_alloc.restype = C.c_int

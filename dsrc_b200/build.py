@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRCS = ["api.cu", "parse.cu", "tags.cu", "rc_model.cu", "q0.cu", "finish.cu", "decode.cu", "synth.cu", "crc.cu"]
+SRCS = ["api.cu", "parse.cu", "tags.cu", "rc_model.cu", "q0.cu", "finish.cu", "decode.cu", "synth.cu", "crc.cu", "container.cpp"]
 LIB = os.path.join(HERE, "libdsrc_b200.so")
 
 

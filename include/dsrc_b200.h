@@ -101,6 +101,19 @@ uint32_t dsrcgpu_tag_capacity_after(uint32_t capacity_before, uint32_t n_fields)
  * (CLI: -b MB << 20). Pure host function. Returns the number of blocks (only the first max_blocks are stored). */
 uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks);
 
+/* == FastqParser::Analyze (src/FastqParser.cpp:27-138) on the first chunk: fills plus_repetition / color_space and, when
+ * ds->quality_offset is 0 on entry, the auto-detected quality offset. DSRCGPU_E_MALFORMED == "Error analyzing FASTQ dataset". Pure host. */
+int dsrcgpu_analyze_first_chunk(const uint8_t* chunk, uint64_t size, dsrcgpu_dataset_t* ds);
+
+/* == DsrcFileWriter::WriteFileHeader / WriteFileFooter (src/DsrcFile.cpp:112-170) and DsrcFileReader::ReadFileHeader / ReadFileFooter
+ * (:264-314): archive = 40-byte header | blocks back to back | footer. Pure host. */
+uint64_t dsrcgpu_archive_footer_size(uint64_t n_blocks);
+int dsrcgpu_write_archive_header(uint8_t* out40, uint64_t n_blocks, uint64_t blocks_total_bytes);
+int dsrcgpu_write_archive_footer(uint8_t* out, uint64_t out_cap, const uint32_t* block_sizes, uint64_t n_blocks,
+                                 const dsrcgpu_dataset_t* ds, const dsrcgpu_settings_t* cs);
+int dsrcgpu_read_archive_index(const uint8_t* arc, uint64_t size, uint64_t* n_blocks, uint64_t* blk_off, uint32_t* blk_len,
+                               uint64_t max_blocks, dsrcgpu_dataset_t* ds, dsrcgpu_settings_t* cs);
+
 /* device-timed duration (ms, CUDA events on the context's stream) of the last encode/decode call */
 float dsrcgpu_last_call_ms(dsrcgpu_ctx* ctx);
 

@@ -126,3 +126,38 @@ def test_two_ranks_over_gloo_assemble_the_reference_archive():
     big = synth.illumina(6000, seed=21, small_field=True)
     assert bytes(out) == refbind.Oracle().compress(big, 2, 2, 1 << 18, 0)
     assert res[1][2] > 40 and len(res[1][3]) > 0
+
+
+def test_c_abi_format_helpers_match_oracle():
+    """dsrcgpu_analyze_first_chunk / write_archive_header / write_archive_footer / read_archive_index (pure host C)"""
+    import ctypes as C
+    from dsrc_b200 import _lib
+    L = _lib.lib()
+    o = refbind.Oracle()
+    for data in [synth.illumina(50, seed=1), synth.illumina(40, seed=2, plus_rep=True), synth.ion454(30, seed=3)]:
+        ok, q, pr, cs = o.analyze(data[:-1])
+        ds = _lib.Dataset(0, 0, 0)
+        assert L.dsrcgpu_analyze_first_chunk(data[:-1], len(data) - 1, C.byref(ds)) == 0
+        assert (ds.quality_offset, bool(ds.plus_repetition), bool(ds.color_space)) == (q, pr, cs)
+    assert L.dsrcgpu_analyze_first_chunk(b"@a\nAC\n+\nII", 10, C.byref(_lib.Dataset(0, 0, 0))) != 0      # a single record: reference refuses
+    big = synth.illumina(8000, seed=7)
+    for crc in (False, True):
+        arc = refbind.Oracle().compress(big, 2, 2, 1 << 20, 0, crc=crc)
+        n = C.c_uint64()
+        off = np.zeros(16, dtype=np.uint64)
+        ln = np.zeros(16, dtype=np.uint32)
+        ds = _lib.Dataset(0, 0, 0)
+        cs = _lib.Settings(0, 0, 0, 0, 0)
+        assert L.dsrcgpu_read_archive_index(arc, len(arc), C.byref(n), off.ctypes.data_as(_lib.u64p), ln.ctypes.data_as(_lib.u32p), 16, C.byref(ds), C.byref(cs)) == 0
+        nb = n.value
+        assert (ds.quality_offset, cs.dna_order, cs.quality_order, bool(cs.calc_crc32)) == (33, 6, 2, crc)
+        total = int(ln[:nb].astype(np.uint64).sum())
+        hdr = (C.c_uint8 * 40)()
+        assert L.dsrcgpu_write_archive_header(hdr, nb, total) == 0
+        assert bytes(hdr) == arc[:40]
+        fs = L.dsrcgpu_archive_footer_size(nb)
+        foot = (C.c_uint8 * fs)()
+        assert L.dsrcgpu_write_archive_footer(foot, fs, ln.ctypes.data_as(_lib.u32p), nb, C.byref(ds), C.byref(cs)) == 0
+        assert bytes(foot) == arc[40 + total:]
+        assert int(off[0]) == 40 and int(off[nb - 1]) + int(ln[nb - 1]) == 40 + total
+    assert L.dsrcgpu_read_archive_index(b"\0" * 64, 64, C.byref(n), None, None, 0, None, None) != 0
