@@ -62,12 +62,8 @@ __device__ void dna_cfg(u32 order, u32 scheme, ModelCfg& c)
 
 #define TRIP(f, cum, tot) ((u64)(f) | ((u64)(cum) << 16) | ((u64)(tot) << 32))
 #define PROF_MARK(slot) do { if (ws.prof && threadIdx.x == 0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&ws.prof[slot], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
-#ifndef QDIRECT_ON
-#define QDIRECT_ON 1
-#endif
 #include "model_tab.cuh"
 #include "model_dna.cuh"
-#include "model_qdirect.cuh"
 
 struct ModelShared {
     union {
@@ -78,7 +74,6 @@ struct ModelShared {
         } g;
         TabShared tab;                             // tile/table engine (model_tab.cuh)
         DnaDirectShared dna;                       // shared-memory table engine of the 4-symbol DNA model (model_dna.cuh)
-        QDirectShared qd;                          // direct engine of the 16-symbol quality model (model_qdirect.cuh)
     } u;
     u32 scan[DSRC_WARPS + 1];
     u32 n_long, n_heads;
@@ -406,22 +401,6 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
         u8* pc = (u8*)bufB;
         u32 fixed_len = 0;
         const bool tabpath = cfg.alpha <= 16 && ws.tab != nullptr;
-        const bool qdirect = QUALITY && tabpath && cfg.alpha == 16 && QDIRECT_ON;
-        if (qdirect) {
-            u32 flen = (st.min_len == st.max_len && st.max_len > 0 && st.max_len <= 1024) ? st.max_len : 0u;
-            if (!flen) {
-                const RecArrays& R = ws.rec;
-                for (u32 r = warp_id(); r < st.n_rec; r += DSRC_WARPS) {
-                    const u32 len = R.qua_len[d.rec_base + r], qo = R.qcat_off[d.rec_base + r];
-                    for (u32 j = lane_id(); j < len; j += 32) pc[qo + j] = (u8)(j * cfg.rescale / len);
-                }
-                __syncthreads();
-            }
-            quality_direct_engine(S.u.qd, S.rank, ws.qcat + d.sym_base, pc, flen, cfg.rescale, M, cfg.sym_order, cfg.bits,
-                                  ws.tab + (u64)blockIdx.x * ws.tab_stride, (u32*)bufA, trip, ws.prof);
-            PROF_MARK(prof_base + 7);
-            continue;
-        }
         if (QUALITY && tabpath && st.min_len == st.max_len && st.max_len > 0 && st.max_len <= 1024) {
             // one read length in the block: position bucket j * rescale / len (TTranslationalQualityEncoder::Encode :307) from a small table
             fixed_len = st.max_len;

@@ -53,3 +53,14 @@ def test_archive_with_crc32_matches_reference():
     assert arc == refbind.Oracle().compress(big, 2, 2, 1 << 20, 0, crc=True)
     assert hashlib.sha256(arc).hexdigest() == GOLD["archives"]["illumina8000_seed7_d2_q2_b1_crc"]["archive_sha256"]
     assert DsrcDecompressorMT().process(arc) == big
+
+
+def test_archive_8mb_blocks_reference_default():
+    """-b8 (the reference's default buffer): one 8 MB block plus a remainder, -d2 -q2 and -d0 -q0"""
+    from dsrc_b200 import DsrcCompressorMT, DsrcDecompressorMT, InputParameters
+    big = synth.illumina(26000, seed=71)
+    assert len(big) > (8 << 20)
+    for dl, ql in [(2, 2), (0, 0)]:
+        arc, _ = DsrcCompressorMT().process(InputParameters(dl, ql, 8, 0), big)
+        assert arc == refbind.Oracle().compress(big, dl, ql, 8 << 20, 0)
+        assert DsrcDecompressorMT().process(arc) == big
