@@ -46,8 +46,10 @@ static __device__ u32 huf_build_warp(const u32* freq, u32 n_in, HufWork* w, u32*
     u32 cnt = n;
     {
         u64 m = huf_warp_argmin(w, cnt);
-        if (cnt == 2 && (m >> 20) == 0) {             // :128-133
-            if (ln == 0) { u32 i = (u32)(m & 1023); w->wfreq[i] = 1; if (w->wfreq[1 - i] == 0) w->wfreq[1 - i] = 1; }
+        if (cnt == 2 && (m >> 20) == 0) {             // :128-133: the reference forces both frequencies to >= 1 in place, without
+            // re-heapifying: the former minimum stays heap[0] and becomes the LEFT child even if the other symbol is smaller and
+            // also has frequency 1. Leaving the minimum's key at 0 keeps that order (the merged frequency of the only merge is unused).
+            if (ln == 0) { u32 i = (u32)(m & 1023); if (w->wfreq[1 - i] == 0) w->wfreq[1 - i] = 1; }
             __syncwarp();
         } else {
             // :134-138 -- drop zero-frequency symbols (ascending symbol order) while more than two remain.

@@ -183,8 +183,10 @@ static void huf_build(huf_t* h, const u32* freq_in, u32 n_in) /* Restart+Insert*
     {
         u32 m;
         HUF_MIN_IDX(m);
-        if (cnt == 2 && hf[m] == 0) { /* huffman.cpp:128-133 */
-            hf[m] = 1;
+        if (cnt == 2 && hf[m] == 0) { /* huffman.cpp:128-133: both frequencies are forced to >= 1 IN PLACE, without re-heapifying,
+                                       * so the element that was the minimum stays heap[0] and becomes the LEFT child even when the
+                                       * other symbol is smaller and also has frequency 1. Keeping the minimum's key at 0 here
+                                       * reproduces that order (with two symbols the merged frequency is never used). */
             if (hf[1 - m] == 0) hf[1 - m] = 1;
         } else {
             for (;;) {           /* :136 drop zero-frequency symbols while more than two remain */
@@ -1261,7 +1263,8 @@ int64_t dsrc_oracle_read(dsrc_oracle_t* o, const u8* blk, u64 size, u8* out, u64
                                 v = f->hg ? hufd_get(f->hg, &r) : br_bits(&r, f->bits_num);
                                 v += f->scheme == 3 ? (u32)prev[j] + (u32)f->min_delta : (u32)f->min_value;
                         }
-                        NEED(tl + 12); tl += num_to_str(t + tl, v); prev[j] = (i32)v; t[tl++] = f->sep; continue;
+                        { u8 num[12]; u32 nl = num_to_str(num, v); NEED(tl + nl + 1); memcpy(t + tl, num, nl); tl += nl; }
+                        prev[j] = (i32)v; t[tl++] = f->sep; continue;
                     }
                     {
                         u32 fl_len = f->is_len_constant ? f->len : br_bits(&r, f->bits_len) + f->min_len;

@@ -1,6 +1,10 @@
 """Shared parity-case catalogue: (name, fastq bytes, dna_order, quality_order, plus_rep).
 dna_order = 3 * CLI -d level, quality_order = CLI -q level (src/DsrcOperator.h:74-90)."""
+import os
+
 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def small_cases():
@@ -35,4 +39,9 @@ def small_cases():
     rq = synth.random_quals(1500)
     for d, q in [(6, 2), (9, 1)]:
         c.append(("randq60_d%d_q%d" % (d, q), rq, d, q, 0))
+    # inputs found by tools/fuzz_parity.py: a two-symbol Huffman tree whose zero-frequency symbol is the larger one (the reference
+    # forces both frequencies to 1 in place, src/huffman.cpp:128-133, so the former minimum stays the left child), and very short
+    # variable-length reads with '+' title repetition
+    c.append(("fuzz_huffman_two_symbol_tie_d3_q0", open(os.path.join(GOLDEN_DIR, "fuzz_huffman_two_symbol_tie.fq"), "rb").read(), 3, 0, 1))
+    c.append(("fuzz_short_reads_d6_q2", open(os.path.join(GOLDEN_DIR, "fuzz_short_reads.fq"), "rb").read(), 6, 2, 0))
     return c
