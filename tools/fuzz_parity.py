@@ -19,10 +19,10 @@ ALNUM = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789"
 def rand_case(rng):
     n = int(rng.choice([1, 2, 3, 7, 40, 150, 400]))
     # ---- title template: a list of field generators
-    nf = int(rng.integers(1, 9))
+    nf = int(rng.integers(1, 9)) if rng.random() < 0.8 else int(rng.integers(9, 24))
     fields = []
     for f in range(nf):
-        kind = rng.choice(["const", "counter", "randnum", "smallnum", "text", "vartext", "runnum"])
+        kind = rng.choice(["const", "counter", "randnum", "smallnum", "text", "vartext", "runnum", "zeronum", "bignum", "downcount", "longtext"])
         fields.append((kind, int(rng.integers(1, 9)), int(rng.integers(0, 1000))))
     seps = [SEPS[int(rng.integers(0, len(SEPS)))] for _ in range(nf - 1)]
     consts = [bytes(ALNUM[int(x)] for x in rng.integers(0, 52, size=int(rng.integers(1, 6)))) for _ in range(nf)]
@@ -49,6 +49,14 @@ def rand_case(rng):
                 if rng.random() < 0.1:
                     run_val = int(rng.integers(0, 50))
                 parts.append(b"%d" % (run_val + 1))
+            elif kind == "zeronum":                    # leading zeros: not numeric for the reference (utils.h:163-175)
+                parts.append(b"%04d" % int(rng.integers(0, 3000)))
+            elif kind == "bignum":
+                parts.append(b"%d" % int(rng.integers(1, 2 ** 29)))      # differences stay below 2^31: bit_length() returns 64 beyond, undefined upstream
+            elif kind == "downcount":
+                parts.append(b"%d" % max(1, 100000 - i * (a + 1) - int(rng.integers(0, 2))))
+            elif kind == "longtext":
+                parts.append(bytes(ALNUM[int(x)] for x in rng.integers(0, 4, size=int(rng.integers(100, 160)))))
             elif kind == "text":
                 parts.append(bytes(ALNUM[int(x)] for x in rng.integers(0, 8 + a, size=a)))
             else:
@@ -78,6 +86,8 @@ def rand_case(rng):
             q[j] = int(rng.integers(0, 7)) if (c == ord("N") and rng.random() < 0.8) else max(int(q[j]), 7)
         out.append(title + b"\n" + seq.tobytes() + b"\n+" + (title[1:] if plus_rep else b"") + b"\n" + (q + 33).astype(np.uint8).tobytes() + b"\n")
     data = b"".join(out)
+    if rng.random() < 0.1 and not plus_rep:
+        data = data.replace(b"\n", b"\r\n")
     d = int(rng.choice([0, 3, 6, 9]))
     qq = int(rng.choice([0, 1, 2]))
     # keep inside the envelope where the reference is defined
@@ -102,7 +112,9 @@ def main():
     bad = 0
     for it in range(n):
         data, d, q, pr, crc = rand_case(rng)
-        chunk = data[:-1]
+        chunk = data[:-2] if data.endswith(b"\r\n") else data[:-1]
+        if data.endswith(b"\r\n"):
+            data = data.replace(b"\r\n", b"\n")     # decode always writes LF
         try:
             o = refbind.Oracle(33, pr, d, q, crc=crc)
             a1, ra, ca = o.store(chunk)
@@ -111,6 +123,21 @@ def main():
             print("case", it, "oracle refused:", e)
             continue
         if mode == "cpu":
+            # the reference has undefined behaviour on some inputs (it may crash): each case runs in a forked child
+            pid = os.fork()
+            if pid:
+                _, st = os.waitpid(pid, 0)
+                if os.WIFSIGNALED(st):
+                    print("case", it, "reference crashed (signal %d): outside its defined envelope" % os.WTERMSIG(st))
+                    continue
+                code = os.WEXITSTATUS(st)
+                if code:
+                    bad += 1
+                    path = os.path.join(ROOT, "gpurun_out", "fuzz_%s_%d_%d.fq" % (mode, seed, it))
+                    os.makedirs(os.path.dirname(path), exist_ok=True)
+                    open(path, "wb").write(data)
+                    print("MISMATCH case", it, "d", d, "q", q, "plus_rep", pr, "crc", crc, "->", path)
+                continue
             r = refbind.Ref(33, pr, d, q, crc=crc)
             b1, rb, cb = r.store(chunk)
             b2, _, _ = r.store(chunk)
@@ -123,6 +150,8 @@ def main():
             except RuntimeError as e:
                 print('case', it, 'read failed:', e)
                 ok = False
+            sys.stdout.flush()
+            os._exit(0 if ok else 1)
         else:
             from dsrc_b200 import BlockCompressor, DsrcGpuError
             bc = BlockCompressor(33, bool(pr), d, q, max_block_bytes=max(len(chunk) + 64, 1 << 16), calc_crc32=crc)
