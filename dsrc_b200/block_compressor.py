@@ -73,16 +73,20 @@ class BlockCompressor:
         elif not warm:
             caps = self._tagcaps(data, offs, lens)
         buf = np.frombuffer(data, dtype=np.uint8)
-        cap = int(lens_a.astype(np.uint64).sum()) * 3 // 2 + 4096 * n + 65536
-        out = np.empty(cap, dtype=np.uint8)
+        cap = int(lens_a.astype(np.uint64).sum()) * 3 // 2 + 8192 * n + (2 << 20)
         sizes = np.zeros(n, dtype=np.uint32)
         raw = np.zeros((n, 4), dtype=np.uint64)
         cmp_ = np.zeros((n, 4), dtype=np.uint64)
-        rc = self.L.dsrcgpu_encode_blocks(
-            self.h, buf.ctypes.data_as(C.c_void_p), offs_a.ctypes.data_as(_lib.u64p), lens_a.ctypes.data_as(_lib.u32p),
-            caps.ctypes.data_as(_lib.u32p) if caps is not None else None, n,
-            out.ctypes.data_as(C.c_void_p), cap, sizes.ctypes.data_as(_lib.u32p),
-            raw.ctypes.data_as(_lib.u64p), cmp_.ctypes.data_as(_lib.u64p))
+        for attempt in range(4):       # tiny blocks with long read-ID fields can expand (many Huffman trees in the tag header)
+            out = np.empty(cap, dtype=np.uint8)
+            rc = self.L.dsrcgpu_encode_blocks(
+                self.h, buf.ctypes.data_as(C.c_void_p), offs_a.ctypes.data_as(_lib.u64p), lens_a.ctypes.data_as(_lib.u32p),
+                caps.ctypes.data_as(_lib.u32p) if caps is not None else None, n,
+                out.ctypes.data_as(C.c_void_p), cap, sizes.ctypes.data_as(_lib.u32p),
+                raw.ctypes.data_as(_lib.u64p), cmp_.ctypes.data_as(_lib.u64p))
+            if rc != -3:
+                break
+            cap *= 4
         if rc != 0:
             raise self._err(rc)
         blocks = []

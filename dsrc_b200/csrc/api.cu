@@ -45,6 +45,7 @@ struct Slot {
     BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
     cudaEvent_t ev_results = nullptr, ev_sizes = nullptr;
     bool busy = false; u32 first = 0, cnt = 0, batch = 0;
+    Workspace ws{};                                          // of the batch in flight (re-used if its output staging has to grow)
     std::vector<u64> offs;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
     void release()
@@ -334,6 +335,7 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(sl.ev_results, s));
     CK(cudaGetLastError());
+    sl.ws = ws;
     return DSRCGPU_OK;
 }
 
@@ -368,6 +370,20 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         CK(cudaEventSynchronize(t.ev_results));
         collect_times(ctx, &t);
         u64 end = on_device ? out_pos : 0;
+        if (!on_device) {
+            // tiny blocks with long read-ID fields can come out LARGER than the staging estimate (hundreds of Huffman trees in the
+            // tag header): the streams are still in the slot, so grow the staging buffer and repeat only the size scan + gather
+            bool grow = false; u64 need = 0;
+            for (u32 i = 0; i < t.cnt; ++i) { if (t.h_result[i].status & 0x100) grow = true; need += t.h_result[i].total_size; }
+            if (grow) {
+                CK(t.out.ensure(need + 64));
+                t.ws.out = (u8*)t.out.p; t.ws.out_cap = need + 64;
+                launch_meta_and_sizes(t.ws, t.stream, 0, nullptr);
+                launch_gather(t.ws, t.stream);
+                CK(cudaMemcpyAsync(t.h_result, t.result.p, sizeof(BlockResult) * t.cnt, cudaMemcpyDeviceToHost, t.stream));
+                CK(cudaStreamSynchronize(t.stream));
+            }
+        }
         for (u32 i = 0; i < t.cnt; ++i) {
             const BlockResult& br = t.h_result[i];
             if (br.status != ST_OK) return status_to_error(ctx, br.status, t.first + i);

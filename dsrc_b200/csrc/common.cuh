@@ -27,7 +27,7 @@ enum : u32 {
 #define TAG_MAX_FIELDS 64
 #define TAG_STAT_LEN 128        // Field::MAX_FIELD_STAT_LEN (src/TagModeler.h:27)
 #define TAG_NUM_HUF 512         // Field::MAX_NUM_VAL_HUF
-#define TAG_TEXT_SLOTS 160      // Huffman slots (256 symbols) per block for text-field positions
+#define TAG_TEXT_SLOTS 640      // Huffman slots (256 symbols) per block for text-field positions (five 128-position fields)
 #define TAG_NUM_SLOTS 8         // Huffman slots (512 symbols) per block for ValueVar/DeltaVar fields
 
 // host-filled description of one block of a batch

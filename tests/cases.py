@@ -43,5 +43,10 @@ def small_cases():
     # forces both frequencies to 1 in place, src/huffman.cpp:128-133, so the former minimum stays the left child), and very short
     # variable-length reads with '+' title repetition
     c.append(("fuzz_huffman_two_symbol_tie_d3_q0", open(os.path.join(GOLDEN_DIR, "fuzz_huffman_two_symbol_tie.fq"), "rb").read(), 3, 0, 1))
+    # read IDs with two 100-160 character text fields: > 256 per-position Huffman trees in the tag header, the compressed block is
+    # larger than the input
+    lt = open(os.path.join(GOLDEN_DIR, "fuzz_long_text_fields.fq"), "rb").read()
+    c.append(("fuzz_long_text_fields_d6_q2", lt, 6, 2, 0))
+    c.append(("fuzz_long_text_fields_d0_q0", lt, 0, 0, 0))
     c.append(("fuzz_short_reads_d6_q2", open(os.path.join(GOLDEN_DIR, "fuzz_short_reads.fq"), "rb").read(), 6, 2, 0))
     return c
