@@ -125,3 +125,16 @@ def random_quals(n_reads, length=150, seed=9, n_levels=60):
     seq = BASES[rng.integers(0, 4, size=(n_reads, length))]
     qual = (rng.integers(0, n_levels, size=(n_reads, length)) + 33).astype(np.uint8)
     return b"".join(b"@RQ.%d\n" % (i + 1) + seq[i].tobytes() + b"\n+\n" + qual[i].tobytes() + b"\n" for i in range(n_reads))
+
+
+def changing_titles(seed=12):
+    """a file whose title structure changes between blocks: 4-field titles (the reference's field vector ends at capacity 4), then
+    13-field Illumina titles (the vector grows 4 -> 8 -> 16 in the middle of a block's first title), then 454-style titles --
+    SURVEY 8-Q1 in its general form (capacity carried across blocks in file order)."""
+    rng = np.random.default_rng(seed)
+    a = []
+    for i in range(4200):
+        s = BASES[rng.integers(0, 4, size=100)]
+        q = (rng.integers(20, 41, size=100) + 33).astype(np.uint8)
+        a.append(b"@r%d/%d x=%d\n" % (i + 1, 1 + i % 2, int(rng.integers(0, 19))) + s.tobytes() + b"\n+\n" + q.tobytes() + b"\n")
+    return b"".join(a) + illumina(3200, seed=seed + 1, small_field=True) + ion454(1500, seed=seed + 2)

@@ -64,3 +64,12 @@ def test_archive_8mb_blocks_reference_default():
         arc, _ = DsrcCompressorMT().process(InputParameters(dl, ql, 8, 0), big)
         assert arc == refbind.Oracle().compress(big, dl, ql, 8 << 20, 0)
         assert DsrcDecompressorMT().process(arc) == big
+
+
+def test_archive_changing_title_structure():
+    """field-vector capacity carried across blocks with different field counts (general form)"""
+    from dsrc_b200 import DsrcCompressorMT, DsrcDecompressorMT, InputParameters
+    big = synth.changing_titles()
+    arc, _ = DsrcCompressorMT().process(InputParameters(2, 2, 1, 0), big)
+    assert arc == refbind.Oracle().compress(big, 2, 2, 1 << 20, 0)
+    assert DsrcDecompressorMT().process(arc) == big

@@ -92,3 +92,14 @@ def test_crc32_blocks_and_archive_match_reference(tmp_path):
     arc = dst.read_bytes()
     assert arc == refbind.Oracle().compress(big, 2, 2, 1 << 20, 0, crc=True)
     assert refbind.Oracle().decompress(arc, len(big) + 64) == big
+
+
+def test_changing_title_structure_matches_reference_cli_path(tmp_path):
+    """Q1 in general form: the capacity of TagStats::fields evolves across blocks whose first titles have different field counts"""
+    import synth
+    big = synth.changing_titles()
+    src = tmp_path / "in.fq"
+    src.write_bytes(big)
+    dst = tmp_path / "o.dsrc"
+    assert refbind.Ref().compress_file(str(src), str(dst), 2, 2, 1, 1, 0) == 0
+    assert dst.read_bytes() == refbind.Oracle().compress(big, 2, 2, 1 << 20, 0)
