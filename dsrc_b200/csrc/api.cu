@@ -548,8 +548,9 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
     // are latency bound, so throughput is the number of chains); a chain that fills its hash retries in the next tier
     u64 tier0 = 512ull << 10;
     if (const char* e = getenv("DSRCGPU_DEC_ARENA_KB")) tier0 = std::max<u64>(64, (u64)atoll(e)) << 10;
-    const u64 tiers[3] = {tier0, std::max<u64>(tier0, 8ull << 20), std::max<u64>(big, 8ull << 20)};
-    const u32 pools[3] = {8192u, 65536u, 262144u};        // Huffman nodes (8 B) per block
+    const int NT = 4;
+    const u64 tiers[NT] = {tier0, std::max<u64>(tier0, 3ull << 20), std::max<u64>(tier0, 16ull << 20), std::max<u64>(big, 16ull << 20)};
+    const u32 pools[NT] = {8192u, 32768u, 131072u, 262144u};        // Huffman nodes (8 B) per block
     const u64 budget = 24ull << 30;
     int start_tier = 0;                                   // raised when most blocks of a batch had to retry (large-alphabet data)
     u32 dec_batch = 32768;
@@ -614,7 +615,7 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
             if (status[i] != ST_OK) { int e = status_to_error(ctx, status[i], first + i); if (e == DSRCGPU_E_MALFORMED) ctx->err += " (corrupt compressed block)"; return e; }
         }
         const size_t n_retry0 = retry.size();
-        for (int tier = start_tier + 1; tier < 3 && !retry.empty(); ++tier) {
+        for (int tier = start_tier + 1; tier < NT && !retry.empty(); ++tier) {
             const u32 group = (u32)std::max<u64>(1, budget / (tiers[tier] + (u64)pools[tier] * 8));
             std::vector<u32> again;
             for (size_t g0 = 0; g0 < retry.size(); g0 += group) {
@@ -624,7 +625,7 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
                 rc = decode_batch(ctx, sl, d_in, gi.data(), go.data(), blk_len, goo.data(), gn, d_out, cap, tiers[tier], pools[tier], gs.data(), gz.data());
                 if (rc) return rc;
                 for (u32 k = 0; k < gn; ++k) {
-                    if (gs[k] == DEC_ST_RETRY && tier < 2) again.push_back(retry[g0 + k]);
+                    if (gs[k] == DEC_ST_RETRY && tier < NT - 1) again.push_back(retry[g0 + k]);
                     else if (gs[k] != ST_OK) return status_to_error(ctx, gs[k], gi[k]);
                 }
             }

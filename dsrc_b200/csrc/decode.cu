@@ -254,17 +254,17 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_tags(Workspace ws, uint2* pool_
 
 // ---- adaptive rows of a decoding chain ----
 struct RowStore {
-    u8* base; u32 slot_bytes, row_off, mask, shift, used, limit; bool direct, fail;
+    u8* base; u32 slot_bytes, row_off, cap, used, limit; bool direct, fail;
     __device__ void setup(u8* arena, u64 arena_bytes, u32 N, u32 key_bits)
     {
         base = arena; used = 0; fail = false;
         const u64 table = ((u64)2 * N) << key_bits;
-        if (table <= arena_bytes) { direct = true; slot_bytes = 2 * N; row_off = 0; mask = 0; shift = 0; limit = 0; return; }
+        if (table <= arena_bytes) { direct = true; slot_bytes = 2 * N; row_off = 0; cap = 0; limit = 0; return; }
         direct = false;
-        u32 sb = 16; while (sb < 2 * N + 4) sb <<= 1;       // slot: u32 key, row in the upper part
-        slot_bytes = sb; row_off = sb >= 2 * N * 2 ? sb / 2 : sb - 2 * N;
-        u32 lg = 0; while (((u64)sb << (lg + 1)) <= arena_bytes) ++lg;
-        mask = (1u << lg) - 1; shift = 32 - lg; limit = (u32)(((u64)1 << lg) * 7 / 8);
+        row_off = 16;                                        // slot: u32 key in a 16-byte header, then the 16-byte aligned row
+        slot_bytes = 16 + ((2 * N + 15) & ~15u);
+        cap = (u32)(arena_bytes / slot_bytes);
+        limit = (u32)((u64)cap * 7 / 8);
     }
     // returns the row of ctx; fresh = the row has not been touched by this block (contents undefined: treat as all ones)
     __device__ __forceinline__ u16* row(u32 ctx, bool& fresh)
@@ -274,10 +274,10 @@ struct RowStore {
             fresh = p[0] == 0;                              // counters never drop below 1; the arena is zeroed per batch
             return p;
         }
-        u32 h = (ctx * 0x9E3779B1u) >> shift;
+        u32 h = __umulhi(ctx * 0x9E3779B1u, cap);           // multiplicative hash, range-reduced to [0, cap)
         for (;;) {
             u8* s = base + (u64)h * slot_bytes;
-            if (row_off >= 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(s + row_off));   // row sector in flight together with the key sector
+            if (slot_bytes > 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(s + 32));   // the rest of the row in flight together with the key
             const u32 key = *(u32*)s;
             if (key == ctx + 1) { fresh = false; return (u16*)(s + row_off); }
             if (key == 0) {
@@ -285,7 +285,7 @@ struct RowStore {
                 fresh = true;
                 return (u16*)(s + row_off);
             }
-            h = (h + 1) & mask;
+            if (++h == cap) h = 0;
         }
     }
 };
