@@ -338,7 +338,7 @@ def main():
     # device-resident, verified byte for byte against the input
     dec = None
     if not args.no_decode:
-        nd = min(n, 32768)
+        nd = min(n, 65536)
         step_device()
         L.dsrcgpu_release_workspace(ctx)      # the encode slots' workspaces make room for the decode chains' arenas
         coffs = np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))[:-1]]).astype(np.uint64)

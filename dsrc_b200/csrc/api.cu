@@ -551,9 +551,10 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
     const int NT = 4;
     const u64 tiers[NT] = {tier0, std::max<u64>(tier0, 3ull << 20), std::max<u64>(tier0, 16ull << 20), std::max<u64>(big, 16ull << 20)};
     const u32 pools[NT] = {8192u, 32768u, 131072u, 262144u};        // Huffman nodes (8 B) per block
-    const u64 budget = 24ull << 30;
+    u64 budget = 32ull << 30;                             // HBM given to the chains' arenas: bounds the chains in flight
+    if (const char* e = getenv("DSRCGPU_DEC_BUDGET_GB")) budget = (u64)std::max(1, atoi(e)) << 30;
     int start_tier = 0;                                   // raised when most blocks of a batch had to retry (large-alphabet data)
-    u32 dec_batch = 32768;
+    u32 dec_batch = 65536;
     if (const char* e = getenv("DSRCGPU_DEC_BATCH")) dec_batch = (u32)std::max(1, atoi(e));
     const u32 per_batch0 = (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / tiers[0]));
     std::vector<u32> idx, status, sizes, retry; std::vector<u64> offs, ooffs;

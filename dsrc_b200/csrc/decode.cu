@@ -607,6 +607,15 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_dna(Workspace ws, uint2* pool_b
         RcDec rc; rc.start(&r);
         u32 hash = 0;
         for (u32 i = 0; i < M && !r.ovr; ++i) {
+            if (rs.direct) {
+                // the rows the next two symbols can meet are contiguous (the new base enters the low bits of the context):
+                // start fetching them now, the chain is otherwise one DRAM round trip per base
+                const u8* nx1 = rs.base + (u64)((hash << bits) & mask) * rs.slot_bytes;
+                const u8* nx2 = rs.base + (u64)((hash << (2 * bits)) & mask) * rs.slot_bytes;
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(nx1));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(nx2));
+                if (alpha == 8) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx2 + 512));
+            }
             bool fresh;
             u16* row = rs.row(hash, fresh);
             if (rs.fail) break;
