@@ -18,6 +18,7 @@
 // thousands of independent chains in flight, each a dozen integer instructions per symbol.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstddef>
 
 #define SORT_MAX_BITS 10                      // radix digits of at most 10 bits: 8 warps x 1024 counters = 32 KB
 #define LONG_T 48                             // context runs longer than this are walked by a whole warp
@@ -65,22 +66,32 @@ __device__ void dna_cfg(u32 order, u32 scheme, ModelCfg& c)
 #include "model_tab.cuh"
 #include "model_dna.cuh"
 
-struct ModelShared {
+union ModelSortShared {
+    u32 H[DSRC_WARPS << SORT_MAX_BITS];        // sort: per-warp digit counters, then scatter offsets
     union {
-        u32 H[DSRC_WARPS << SORT_MAX_BITS];        // sort: per-warp digit counters, then scatter offsets
-        union {
-            struct { u64 tile[SCAN_TILE + SCAN_LOOK]; u16 heads[SCAN_TILE]; u8 cnt[16384]; } t;   // short-run walker
-            struct { u32 B[DSRC_WARPS][128]; u32 P[DSRC_WARPS][128]; } l;                        // long-run walker: per-warp row state
-        } g;
-        TabShared tab;                             // tile/table engine (model_tab.cuh)
-        DnaDirectShared dna;                       // shared-memory table engine of the 4-symbol DNA model (model_dna.cuh)
-    } u;
+        struct { u64 tile[SCAN_TILE + SCAN_LOOK]; u16 heads[SCAN_TILE]; u8 cnt[16384]; } t;   // short-run walker
+        struct { u32 B[DSRC_WARPS][128]; u32 P[DSRC_WARPS][128]; } l;                        // long-run walker: per-warp row state
+    } g;
+};
+// small state first, the per-engine scratch last: the quality kernel never uses the DNA direct engine's 52 KiB and is launched
+// with the smaller footprint (one more CTA per SM)
+struct ModelShared {
     u32 scan[DSRC_WARPS + 1];
     u32 n_long, n_heads;
     u8 rank[256];
     ModelCfg cfg;
     u32 M, ok;
+    union {
+        u32 H[DSRC_WARPS << SORT_MAX_BITS];
+        union {
+            struct { u64 tile[SCAN_TILE + SCAN_LOOK]; u16 heads[SCAN_TILE]; u8 cnt[16384]; } t;
+            struct { u32 B[DSRC_WARPS][128]; u32 P[DSRC_WARPS][128]; } l;
+        } g;
+        TabShared tab;                             // tile/table engine (model_tab.cuh)
+        DnaDirectShared dna;                       // shared-memory table engine of the 4-symbol DNA model (model_dna.cuh)
+    } u;
 };
+#define MODEL_SMEM_QUALITY (offsetof(ModelShared, u) + (sizeof(TabShared) > sizeof(ModelSortShared) ? sizeof(TabShared) : sizeof(ModelSortShared)))
 
 
 // ---- element sources of a sort pass. An element is (ctx << 40) | (sym << 32) | index. A warp walks consecutive rows of
@@ -541,7 +552,7 @@ static void model_smem_optin()
     cudaFuncSetAttribute(k_model<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
     cudaFuncSetAttribute(k_model<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
 }
-void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<true><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
+void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<true><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride); }
 void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
 void launch_rc_encode(const Workspace& ws, cudaStream_t s)
 {
