@@ -130,6 +130,7 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DSRCGPU_E_CUDA; }
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
+    if (settings->dna_order || settings->quality_order) { if (rc_init_device() != cudaSuccess) { delete ctx; return DSRCGPU_E_CUDA; } }
     if (max_inflight_blocks == 0) {
         u64 n = (512ull << 20) / max_block_bytes;          // ~0.5 GiB of FASTQ per batch
         max_inflight_blocks = (u32)std::min<u64>(std::max<u64>(n, 1), 4096);

@@ -10,6 +10,7 @@ void launch_tags(const Workspace& ws, cudaStream_t s, u32 ctas);   // ctas = num
 void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
 void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
 void launch_rc_encode(const Workspace& ws, cudaStream_t s);       // serial range-coder chains, one thread per (block, stream)
+cudaError_t rc_init_device();                                      // fills the reciprocal table of the chains on the current device (once per context)
 // -q0: positional / truncated / RLE Huffman; -d0: 2-bit pack / Huffman. arena: ctas x stride bytes of per-CTA scratch
 void launch_q0_quality(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u32 ctas);
 void launch_d0_dna(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u32 ctas);

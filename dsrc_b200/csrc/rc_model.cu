@@ -472,7 +472,12 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
 // and, for quality, the 256-bit symbol mask of TTranslationalQualityEncoder::Store (QualityEncoder.h:332-342).
 // ------------------------------------------------------------------------------------------------
 #define RC_CTA 64
-__global__ void __launch_bounds__(RC_CTA) k_rc_encode(Workspace ws, u32 do_quality, u32 do_dna)
+#ifndef RC_RING
+#define RC_RING 6
+#endif
+__device__ u32 g_rcp_lut[65536];                     // floor((2^32-1) / tot), filled once per device by k_rcp_lut
+__global__ void k_rcp_lut() { const u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t < 65536) g_rcp_lut[t] = t ? 0xFFFFFFFFu / t : 0u; }
+__global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(Workspace ws, u32 do_quality, u32 do_dna)
 {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 n = ws.n_blocks;
@@ -499,46 +504,69 @@ __global__ void __launch_bounds__(RC_CTA) k_rc_encode(Workspace ws, u32 do_quali
     }
     const u32 M = is_dna ? st.d_total : st.q_total;
     if ((u64)pos + 3ull * M + 24 > cap) { st.status = ST_OVERFLOW; return; }
-    // the chain's triples arrive 4 at a time (one 32-byte sector per load, two sectors in flight); its output bytes leave 8 at a time
+    // the chain's triples arrive 4 at a time (one 32-byte sector per load) through a per-thread ring of RC_RING sectors in shared memory (cp.async), so
+    // ~RC_RING*4 symbols of DRAM latency are covered; its output bytes leave 4 at a time. `range / tot` is the one long-latency
+    // instruction of the chain: the reciprocal floor((2^32-1)/tot) of each symbol's total is fetched from a 64 K-entry table
+    // one sector ahead (off the dependent chain), leaving mulhi + one correction on it. q' = mulhi(range, m) is q or q-1
+    // (m = 2^32/tot - e with 0 < e <= 1, so range*m/2^32 > range/tot - 1), hence a single fix-up is exact.
     const ulonglong2* trip = (const ulonglong2*)((is_dna ? ws.trip_d : ws.trip_q) + d.sym_base);
-    const u32 G = (M + 3) / 4;                         // groups of 4 triples; the arena has >= 16 entries of slack behind M
+    const u32 G = M / 4;                               // full groups of 4 triples; the last M % 4 symbols are coded one by one
     u64 low = 0; u32 range = 0xFFFFFFFFu;
-    u64 obuf = 0; u32 on = pos & 7u;
-    pos &= ~7u;
-    for (u32 k = 0; k < on; ++k) obuf |= (u64)out[pos + k] << (8 * k);
-#define RC_PUT(b) do { obuf |= (u64)(u8)(b) << (8 * on); if (++on == 8) { *(u64*)(out + pos) = obuf; pos += 8; obuf = 0; on = 0; } } while (0)
-#define RC_STEP(tr) do { \
-        const u32 f_ = (u32)(tr) & 0xFFFFu, cum_ = (u32)((tr) >> 16) & 0xFFFFu, tot_ = (u32)((tr) >> 32); \
-        range /= tot_; low += (u64)(range * cum_); range *= f_; \
-        while (range <= 0x00FFFFFFu) { \
-            if ((low ^ (low + range)) & 0xFF00000000000000ull) { const u32 r_ = (u32)low; range = (r_ | 0x00FFFFFFu) - r_; } \
-            RC_PUT(low >> 56); low <<= 8; range <<= 8; \
-        } } while (0)
-    ulonglong2 a0, a1, b0, b1;
-    a0 = a1 = b0 = b1 = make_ulonglong2(0, 0);
-    if (G > 0) { a0 = __ldcs(trip + 0); a1 = __ldcs(trip + 1); }
-    if (G > 1) { b0 = __ldcs(trip + 2); b1 = __ldcs(trip + 3); }
-    u32 i = 0;
-    for (u32 g = 0; g < G; g += 2) {
-        const ulonglong2 c0 = a0, c1 = a1;
-        if (g + 2 < G) { a0 = __ldcs(trip + 2 * (g + 2)); a1 = __ldcs(trip + 2 * (g + 2) + 1); }
-        if (i < M) { RC_STEP(c0.x); ++i; }
-        if (i < M) { RC_STEP(c0.y); ++i; }
-        if (i < M) { RC_STEP(c1.x); ++i; }
-        if (i < M) { RC_STEP(c1.y); ++i; }
-        if (g + 1 >= G) break;
-        const ulonglong2 e0 = b0, e1 = b1;
-        if (g + 3 < G) { b0 = __ldcs(trip + 2 * (g + 3)); b1 = __ldcs(trip + 2 * (g + 3) + 1); }
-        if (i < M) { RC_STEP(e0.x); ++i; }
-        if (i < M) { RC_STEP(e0.y); ++i; }
-        if (i < M) { RC_STEP(e1.x); ++i; }
-        if (i < M) { RC_STEP(e1.y); ++i; }
+    // output: bytes are shifted into a 32-bit word from the top (one PRMT takes the top byte of `low` and inserts it); every
+    // fourth byte the word is complete and in memory order and leaves with one predicated store
+    u32 obuf = 0;
+    {
+        const u32 on = pos & 3u; pos &= ~3u;
+        for (u32 k = 0; k < on; ++k) obuf |= (u32)out[pos + k] << (8 * (4 - on + k));
+        pos += on;
     }
-    for (int k = 0; k < 8; ++k) { RC_PUT(low >> 56); low <<= 8; }
-    for (u32 k = 0; k < on; ++k) out[pos + k] = (u8)(obuf >> (8 * k));
-    st.stream_size[sidx] = pos + on;
+#define RC_PUT_TOP() do { obuf = __byte_perm(obuf, (u32)(low >> 32), 0x7321); ++pos; if ((pos & 3u) == 0) *(u32*)(out + pos - 4) = obuf; } while (0)
+#define RC_STEP(tr, m) do { \
+        const u32 f_ = (u32)(tr) & 0xFFFFu, cum_ = (u32)(tr) >> 16, tot_ = (u32)((tr) >> 32); \
+        u32 q_ = __umulhi(range, (m)); q_ += (range - q_ * tot_ >= tot_) ? 1u : 0u; \
+        low += (u64)(q_ * cum_); range = q_ * f_; \
+        while (range <= 0x00FFFFFFu) { \
+            if ((u32)((low ^ (low + range)) >> 56)) range = ~(u32)low & 0x00FFFFFFu;   /* (r | 0xFFFFFF) - r */ \
+            RC_PUT_TOP(); low <<= 8; range <<= 8; \
+        } } while (0)
+#define RC_RCP(tr) __ldg(&g_rcp_lut[(u32)((tr) >> 32) & 0xFFFFu])
+    __shared__ __align__(16) ulonglong2 ring[RC_RING][2][RC_CTA];       // [slot][half][thread]: conflict-free 16-byte cells
+    const u32 tx = threadIdx.x;
+    auto fetch = [&](u32 g) {                                          // sector g of this chain -> ring slot g % RC_RING (cp.async, L2 only)
+        if (g < G) {
+            const u32 sl = g % RC_RING;
+            const u32 a0 = (u32)__cvta_generic_to_shared(&ring[sl][0][tx]), a1 = (u32)__cvta_generic_to_shared(&ring[sl][1][tx]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(a0), "l"(trip + 2 * g) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(a1), "l"(trip + 2 * g + 1) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");           // one group per sector, empty past the end: uniform counting
+    };
+    for (u32 k = 0; k < RC_RING; ++k) fetch(k);
+    asm volatile("cp.async.wait_group %0;" :: "n"(RC_RING - 1) : "memory");
+    u32 mn0 = 0, mn1 = 0, mn2 = 0, mn3 = 0;
+    if (G) { const ulonglong2 n0 = ring[0][0][tx], n1 = ring[0][1][tx]; mn0 = RC_RCP(n0.x); mn1 = RC_RCP(n0.y); mn2 = RC_RCP(n1.x); mn3 = RC_RCP(n1.y); }
+    for (u32 g = 0; g < G; ++g) {
+        const u32 sl = g % RC_RING, sn = (g + 1) % RC_RING;
+        const ulonglong2 c0 = ring[sl][0][tx], c1 = ring[sl][1][tx];
+        const u32 m0 = mn0, m1 = mn1, m2 = mn2, m3 = mn3;
+        asm volatile("cp.async.wait_group %0;" :: "n"(RC_RING - 2) : "memory");      // sector g+1 has landed
+        if (g + 1 < G) {   // reciprocals of the next sector's totals: in flight while this sector is coded
+            const ulonglong2 n0 = ring[sn][0][tx], n1 = ring[sn][1][tx];
+            mn0 = RC_RCP(n0.x); mn1 = RC_RCP(n0.y); mn2 = RC_RCP(n1.x); mn3 = RC_RCP(n1.y);
+        }
+        fetch(g + RC_RING);                                            // refills the slot just read
+        RC_STEP(c0.x, m0); RC_STEP(c0.y, m1); RC_STEP(c1.x, m2); RC_STEP(c1.y, m3);
+    }
+    for (u32 i = G * 4; i < M; ++i) { const u64 tr = ((const u64*)trip)[i]; const u32 m = RC_RCP(tr); RC_STEP(tr, m); }
+    for (int k = 0; k < 8; ++k) { RC_PUT_TOP(); low <<= 8; }
+    {
+        const u32 on = pos & 3u;
+        for (u32 k = 0; k < on; ++k) out[pos - on + k] = (u8)(obuf >> (8 * (4 - on + k)));
+    }
+    st.stream_size[sidx] = pos;
+#undef RC_RCP
 #undef RC_STEP
-#undef RC_PUT
+#undef RC_PUT_TOP
 }
 
 static u32 model_grid(const Workspace& ws, u32 max_ctas)
@@ -554,6 +582,7 @@ static void model_smem_optin()
 }
 void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<true><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride); }
 void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
+cudaError_t rc_init_device() { k_rcp_lut<<<65536 / 256, 256>>>(); return cudaDeviceSynchronize(); }
 void launch_rc_encode(const Workspace& ws, cudaStream_t s)
 {
     const u32 dq = ws.qua_order > 0, dd = ws.dna_order > 0;
