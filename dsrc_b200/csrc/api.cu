@@ -41,7 +41,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
     DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
-    DevBuf elem_a, elem_b, tagpool, q0_arena, tab;          // per-CTA arenas of the persistent kernels
+    DevBuf elem_a, elem_b, tagpool, q0_arena, queue;        // per-CTA arenas of the persistent kernels, block queue counters
     BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
     cudaEvent_t ev_results = nullptr, ev_sizes = nullptr;
     bool busy = false; u32 first = 0, cnt = 0, batch = 0;
@@ -51,7 +51,7 @@ struct Slot {
     void release()
     {
         DevBuf* bufs[] = {&in, &desc, &state, &result, &probe, &lines, &qcat, &dcat, &trip_q, &trip_d, &ftab, &streams, &out, &r_title_off, &r_seq_off,
-                          &r_qua_off, &r_title_len, &r_qua_len, &r_dna_len, &r_trunc_len, &r_qcat_off, &r_dcat_off, &elem_a, &elem_b, &tagpool, &q0_arena, &tab};
+                          &r_qua_off, &r_title_len, &r_qua_len, &r_dna_len, &r_trunc_len, &r_qcat_off, &r_dcat_off, &elem_a, &elem_b, &tagpool, &q0_arena, &queue};
         for (DevBuf* b : bufs) b->release();
         if (h_desc) cudaFreeHost(h_desc);
         if (h_result) cudaFreeHost(h_result);
@@ -72,6 +72,7 @@ struct dsrcgpu_ctx {
     std::string err;
     Slot slots[MAX_SLOTS]; int n_slots = 1;
     DevBuf prof, cursor, dec_arena;
+    DevBuf tab, tab_mask; u32 tab_count = 0;         // pool of adaptive-row tables shared by all slots (rc_model.cu: tab_acquire)
     u64 tab_stride = 0;
     u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0; u32 q0_ctas = 0; u64 q0_stride = 0;
     // per-kernel timing
@@ -149,13 +150,11 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
             delete ctx; return DSRCGPU_E_CUDA;
         }
     }
-    // persistent model CTAs: 3 per SM (the fourth CTA slot of every SM is left to the range-coder chains of the batch
-    // before), fewer if the sort arenas (2 x 8 B x block/2 entries each) would exceed ~8 GiB per slot
+    // persistent model CTAs: 4 per SM (what the kernels' registers allow; the range-coder chains of other batches fit beside
+    // them), fewer if the sort arenas (2 x 8 B x block/2 entries each) would exceed ~8 GiB per slot
     ctx->model_stride = (u64)max_block_bytes / 2 + 64;
     u64 per_cta = ctx->model_stride * 8 * 2;
-    // several slots run their persistent kernels side by side, so each slot gets its share of the 4 CTA slots per SM
     u64 want = (u64)ctx->sms * 4;
-    if (ctx->n_slots > 1) want = std::max<u64>(ctx->sms, (u64)ctx->sms * 4 * 3 / (2 * ctx->n_slots));
     if (const char* e = getenv("DSRCGPU_MODEL_CTAS")) want = (u64)std::max(1, atoi(e));
     u64 ctas = std::min<u64>(want, std::max<u64>(1, (8ull << 30) / per_cta));
     ctas = std::min<u64>(ctas, max_inflight_blocks);
@@ -178,7 +177,7 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (int i = 0; i < ctx->n_slots; ++i) { if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream); ctx->slots[i].release(); }
-    ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release();
+    ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release(); ctx->tab.release(); ctx->tab_mask.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->call_a) cudaEventDestroy(ctx->call_a);
     if (ctx->call_b) cudaEventDestroy(ctx->call_b);
@@ -301,10 +300,17 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     CK(sl.ftab.ensure(ftab * 8));
     CK(sl.streams.ensure(streams));
     if (rc_q || rc_d) { CK(sl.elem_a.ensure(ctx->model_stride * 8 * ctx->model_ctas)); CK(sl.elem_b.ensure(ctx->model_stride * 8 * ctx->model_ctas)); }
-    if ((rc_q || rc_d) && !sl.tab.p && ctx->tab_stride) {
-        CK(sl.tab.ensure(ctx->tab_stride * ctx->model_ctas));
-        CK(cudaMemsetAsync(sl.tab.p, 0, sl.tab.cap, s));      // invariant between blocks: first counter of every row is 0
+    if ((rc_q || rc_d) && !ctx->tab.p && ctx->tab_stride) {
+        // one table per model CTA that can be resident at a time (4 per SM, the kernels' launch bound), whatever the slot
+        ctx->tab_count = (u32)std::max<u64>(1, std::min<u64>((u64)ctx->sms * 4, (24ull << 30) / ctx->tab_stride));
+        CK(ctx->tab.ensure(ctx->tab_stride * ctx->tab_count));
+        CK(ctx->tab_mask.ensure(((ctx->tab_count + 31) / 32) * 4));
+        CK(cudaMemsetAsync(ctx->tab.p, 0, ctx->tab.cap, s));    // invariant between blocks: first counter of every row is 0
+        CK(cudaMemsetAsync(ctx->tab_mask.p, 0, ctx->tab_mask.cap, s));
+        CK(cudaStreamSynchronize(s));                          // once per context: the other slots' streams use the pool too
     }
+    CK(sl.queue.ensure(8));
+    CK(cudaMemsetAsync(sl.queue.p, 0, 8, s));
     CK(sl.tagpool.ensure(tagpool_bytes_per_block() * ctx->tag_ctas));
     if (!rc_q || !rc_d) CK(sl.q0_arena.ensure(ctx->q0_stride * ctx->q0_ctas));
 
@@ -316,7 +322,8 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     ws.trip_q = (u64*)sl.trip_q.p; ws.trip_d = (u64*)sl.trip_d.p;
     ws.elem_a = (u64*)sl.elem_a.p; ws.elem_b = (u64*)sl.elem_b.p;
     ws.ftab = (u64*)sl.ftab.p; ws.streams = (u8*)sl.streams.p;
-    ws.tab = (u8*)sl.tab.p; ws.tab_stride = ctx->tab_stride;
+    ws.tab = (u8*)ctx->tab.p; ws.tab_stride = ctx->tab_stride; ws.tab_mask = (u32*)ctx->tab_mask.p; ws.tab_count = ctx->tab_count;
+    ws.model_queue = (u32*)sl.queue.p;
     ws.tagpool = (u8*)sl.tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
 
     CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
@@ -668,10 +675,10 @@ extern "C" int dsrcgpu_release_workspace(dsrcgpu_ctx* ctx)
         CK(cudaStreamSynchronize(sl.stream));
         DevBuf* bufs[] = {&sl.in, &sl.desc, &sl.state, &sl.result, &sl.probe, &sl.lines, &sl.qcat, &sl.dcat, &sl.trip_q, &sl.trip_d, &sl.ftab, &sl.streams, &sl.out,
                           &sl.r_title_off, &sl.r_seq_off, &sl.r_qua_off, &sl.r_title_len, &sl.r_qua_len, &sl.r_dna_len, &sl.r_trunc_len, &sl.r_qcat_off, &sl.r_dcat_off,
-                          &sl.elem_a, &sl.elem_b, &sl.tagpool, &sl.q0_arena, &sl.tab};
+                          &sl.elem_a, &sl.elem_b, &sl.tagpool, &sl.q0_arena, &sl.queue};
         for (DevBuf* b : bufs) b->release();
     }
-    ctx->dec_arena.release();
+    ctx->dec_arena.release(); ctx->tab.release(); ctx->tab_mask.release();
     return DSRCGPU_OK;
 }
 

@@ -81,6 +81,7 @@ struct ModelShared {
     u8 rank[256];
     ModelCfg cfg;
     u32 M, ok;
+    u32 blk, tab_id;                               // block fetched from the launch's queue; table taken from the context's pool
     union {
         u32 H[DSRC_WARPS << SORT_MAX_BITS];
         union {
@@ -362,6 +363,29 @@ __device__ void group_scan(ModelShared& S, const u64* sorted, u32* longq, u64* t
     PROF_MARK(prof_base + 4);
 }
 
+// Pool of adaptive-row tables shared by every model CTA of the context (all slots): bit set = table in use. A table is
+// all-zero whenever it is in the pool. The pool holds one table per CTA that can be resident (4 per SM), so a CTA never
+// waits unless tables are held by CTAs of another launch that are still running -- which then finish and release.
+__device__ u32 tab_acquire(u32* mask, u32 count)
+{
+    const u32 words = (count + 31) / 32;
+    u32 w = blockIdx.x % words;
+    for (;;) {
+        for (u32 k = 0; k < words; ++k, w = (w + 1 == words ? 0 : w + 1)) {
+            const u32 valid = (w + 1) * 32 <= count ? 0xFFFFFFFFu : ((1u << (count & 31)) - 1);
+            u32 free = ~*(volatile u32*)&mask[w] & valid;
+            while (free) {
+                const u32 b = __ffs(free) - 1;
+                const u32 old = atomicOr(&mask[w], 1u << b);
+                if (!(old & (1u << b))) { __threadfence(); return w * 32 + b; }
+                free &= ~old & ~(1u << b);
+            }
+        }
+        __nanosleep(200);
+    }
+}
+__device__ void tab_release(u32* mask, u32 id) { atomicAnd(&mask[id >> 5], ~(1u << (id & 31))); }
+
 template <bool QUALITY>
 __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_stride)
 {
@@ -374,10 +398,19 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
     long long prof_t = ws.prof ? clock64() : 0;
     const int prof_base = QUALITY ? 0 : 8;
 
-    for (u32 blk = blockIdx.x; blk < ws.n_blocks; blk += gridDim.x) {
+    // blocks are handed out by a per-launch counter (the CTAs of a launch finish together whatever the blocks cost); the
+    // adaptive-row table of the tile/table engine is taken from the context-wide pool on first need and returned at the end
+    u32* const queue = ws.model_queue + (QUALITY ? 0 : 1);
+    u8* tab = nullptr;
+    auto next_block = [&]() -> u32 {
+        __syncthreads();
+        if (tid == 0) S.blk = atomicAdd(queue, 1u);
+        __syncthreads();
+        return S.blk;
+    };
+    for (u32 blk = next_block(); blk < ws.n_blocks; blk = next_block()) {
         const BlockDesc& d = ws.desc[blk];
         BlockState& st = ws.state[blk];
-        __syncthreads();
         if (st.status != ST_OK) continue;
         // ---- scheme selection
         if (tid == 0) {
@@ -434,7 +467,11 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
         }
         if (tabpath) {
             // ---- tile/table engine (model_tab.cuh)
-            u8* tab = ws.tab + (u64)blockIdx.x * ws.tab_stride;
+            if (!tab) {
+                if (tid == 0) S.tab_id = tab_acquire(ws.tab_mask, ws.tab_count);
+                __syncthreads();
+                tab = ws.tab + (u64)S.tab_id * ws.tab_stride;
+            }
             if (QUALITY) {
                 FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M; f.plut = TS.plut; f.fixed_len = fixed_len; f.jpos = 0;
                 tab_engine<16>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 16);
@@ -464,6 +501,7 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
         // ---- adaptive statistics per context run
         group_scan(S, src, (u32*)dst, trip, M, ws, prof_t, prof_base);
     }
+    if (tab && tid == 0) { __threadfence(); tab_release(ws.tab_mask, S.tab_id); }   // all touched rows are zero again (tab_engine)
 }
 
 // ------------------------------------------------------------------------------------------------
