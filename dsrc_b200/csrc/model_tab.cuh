@@ -23,7 +23,7 @@
 #endif
 
 struct TabShared {
-    u32 el[2][TT];                            // (ctx << 11) | position in tile, ping-pong of the in-tile sort
+    alignas(16) u32 el[2][TT];                // (ctx << 11) | position in tile, ping-pong of the in-tile sort (vector loads)
     u8 sym[TT];
     union { u64 trip[TT]; u16 H[DSRC_WARPS << 10]; } x;   // triple staging / sort counters (never live together)
     // group heads by size class so that the lanes of a warp walk groups of similar length:
@@ -34,6 +34,7 @@ struct TabShared {
     u16 longs[TT / (TAB_LONG + 1) + 2];
     u32 B[DSRC_WARPS][16], P[DSRC_WARPS][16];
     u32 n_heads[3], n_long, n_touched;
+    u32 wv[DSRC_WARPS][4], wcnt[DSRC_WARPS], wflag[DSRC_WARPS];   // scan engine: per-warp aggregates of the segmented scan
     u8 plut[1024];                            // position bucket of every read position when the block's reads have one length
 };
 
@@ -239,6 +240,159 @@ __device__ void tab_long_groups(TabShared& S, const u32* sorted, u32 n, u8* tab,
     }
 }
 
+// ---- scan engine (16-symbol rows): the group walk without a walk.
+// In the sorted tile every context group is a contiguous run in original order. The triple a symbol meets is a function of
+// the group's row at the start of the tile and of the COUNTS of the symbols before it in its run:
+//   freq = row[s] + 2 #(earlier, same symbol), cum = sum_{q<s} row[q] + 2 #(earlier, smaller symbol), tot = sum row + 2 #(earlier)
+// (TSymbolCoderRC::EncodeSymbol, src/SymbolCoderRC.h:35-48, as long as no rescale fires). The counts are an exclusive SEGMENTED
+// prefix sum of one-hot vectors over the sorted tile: 16 byte counters in four words, every thread scans 8 consecutive elements
+// in registers, thread aggregates are combined with a segmented warp scan and a pass over the 8 warp aggregates. No run heads,
+// no size classes, no divergent walks: every lane does the same work whatever the run lengths are. Byte counters are exact
+// for the first 255 members of a run (a count never exceeds the member's position); a run that is longer, or that reaches
+// the rescale threshold of its row, is queued once for the warp-cooperative walker (tab_long_groups), which redoes it from its
+// head -- a few runs per block. The last member of every other run adds the run's counts to the row.
+__device__ __forceinline__ void cnt_add(u32 (&v)[4], u32 s)
+{
+    const u32 inc = 1u << ((s & 3u) * 8), k = s >> 2;
+    v[0] += k == 0 ? inc : 0u; v[1] += k == 1 ? inc : 0u; v[2] += k == 2 ? inc : 0u; v[3] += k == 3 ? inc : 0u;
+}
+__device__ __forceinline__ u32 bytesum(u32 x) { return __vsadu4(x, 0u); }
+
+__device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch, u32 n, u8* tab, u32* touched)
+{
+    const u32 tid = threadIdx.x, ln = lane_id(), w = warp_id();
+    const u32 limit = (1u << 16) - 32;
+    const u32 p0 = tid * 8;
+    const u32 NOKEY = 0x3FFFFFu;                     // not a context (keys have <= 21 bits after the shift)
+    u32 sy = 0, heads = 0, tails = 0;                // per element: symbol (4 bits), "first of its run", "last of its run"
+    {
+        const uint4 a = ((const uint4*)sorted)[tid * 2], b = ((const uint4*)sorted)[tid * 2 + 1];
+        const u32 e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        u32 pk = (p0 && p0 - 1 < n) ? sorted[p0 - 1] >> TT_SHIFT : NOKEY + 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = p0 + j < n;
+            const u32 k = in ? e[j] >> TT_SHIFT : NOKEY;
+            sy |= (in ? (u32)S.sym[e[j] & (TT - 1)] : 0u) << (4 * j);
+            heads |= (k != pk ? 1u : 0u) << j;
+            // the rows P2 will need: on their way into L1 while the counts are scanned
+            if (in && (j == 0 || k != pk)) asm volatile("prefetch.global.L1 [%0];" :: "l"(tab + (u64)k * 32));
+            pk = k;
+        }
+        const u32 nextkey = p0 + 8 < n ? sorted[p0 + 8] >> TT_SHIFT : NOKEY + 2;
+        tails = (heads >> 1) | ((pk != nextkey ? 1u : 0u) << 7);
+    }
+    const u32 nval = p0 < n ? min(8u, n - p0) : 0u;
+
+    // P1: aggregate of this thread's 8 elements (counts since the last run head inside the thread, or of all 8)
+    u32 v[4] = {0u, 0u, 0u, 0u}, cnt = 0, flag = heads ? 1u : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if ((heads >> j) & 1u) { v[0] = v[1] = v[2] = v[3] = 0u; cnt = 0; }
+        cnt_add(v, (sy >> (4 * j)) & 15u); ++cnt;
+    }
+    // segmented inclusive scan over the warp's threads
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 a0 = __shfl_up_sync(FULL, v[0], o), a1 = __shfl_up_sync(FULL, v[1], o), a2 = __shfl_up_sync(FULL, v[2], o), a3 = __shfl_up_sync(FULL, v[3], o);
+        const u32 ac = __shfl_up_sync(FULL, cnt, o), af = __shfl_up_sync(FULL, flag, o);
+        if (ln >= (u32)o) {
+            if (!flag) { v[0] += a0; v[1] += a1; v[2] += a2; v[3] += a3; cnt += ac; }
+            flag |= af;
+        }
+    }
+    if (ln == 31) { S.wv[w][0] = v[0]; S.wv[w][1] = v[1]; S.wv[w][2] = v[2]; S.wv[w][3] = v[3]; S.wcnt[w] = cnt; S.wflag[w] = flag; }
+    // exclusive: what the threads before me accumulated since the last run head
+    u32 c[4], ccnt;
+    {
+        c[0] = __shfl_up_sync(FULL, v[0], 1); c[1] = __shfl_up_sync(FULL, v[1], 1); c[2] = __shfl_up_sync(FULL, v[2], 1); c[3] = __shfl_up_sync(FULL, v[3], 1);
+        ccnt = __shfl_up_sync(FULL, cnt, 1);
+        u32 cflag = __shfl_up_sync(FULL, flag, 1);
+        if (ln == 0) { c[0] = c[1] = c[2] = c[3] = 0u; ccnt = 0; cflag = 0; }
+        __syncthreads();
+        if (!cflag) {                                // no run head in this warp before me: the run continues from earlier warps
+            for (int ww = (int)w - 1; ww >= 0; --ww) {
+                c[0] += S.wv[ww][0]; c[1] += S.wv[ww][1]; c[2] += S.wv[ww][2]; c[3] += S.wv[ww][3]; ccnt += S.wcnt[ww];
+                if (S.wflag[ww]) break;
+            }
+        }
+    }
+
+    // P2: every element meets its row
+    u32 badmask = 0;
+    {
+        u32 T0 = 0;
+        u32* const myscr = scratch + tid * 8;        // exclusive prefix sums of the current row, 16 x u16
+        const u16* P = (const u16*)myscr;
+        v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; v[3] = c[3]; cnt = ccnt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const u32 s = (sy >> (4 * j)) & 15u;
+            const bool head = (heads >> j) & 1u;
+            if (head) { v[0] = v[1] = v[2] = v[3] = 0u; cnt = 0; }
+            if ((u32)j < nval) {
+                const u32 e = sorted[p0 + j];
+                if (j == 0 || head) {
+                    const uint4* rowp = (const uint4*)(tab + (u64)(e >> TT_SHIFT) * 32);
+                    uint4 r0 = rowp[0], r1 = rowp[1];
+                    if ((r0.x & 0xFFFFu) == 0) { r0 = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u); r1 = r0; }
+                    u32 o = 0; uint4 ex;
+                    ex.x = o * 0x10001u + (r0.x << 16); o += (r0.x & 0xFFFFu) + (r0.x >> 16);
+                    ex.y = o * 0x10001u + (r0.y << 16); o += (r0.y & 0xFFFFu) + (r0.y >> 16);
+                    ex.z = o * 0x10001u + (r0.z << 16); o += (r0.z & 0xFFFFu) + (r0.z >> 16);
+                    ex.w = o * 0x10001u + (r0.w << 16); o += (r0.w & 0xFFFFu) + (r0.w >> 16);
+                    ((uint4*)myscr)[0] = ex;
+                    ex.x = o * 0x10001u + (r1.x << 16); o += (r1.x & 0xFFFFu) + (r1.x >> 16);
+                    ex.y = o * 0x10001u + (r1.y << 16); o += (r1.y & 0xFFFFu) + (r1.y >> 16);
+                    ex.z = o * 0x10001u + (r1.z << 16); o += (r1.z & 0xFFFFu) + (r1.z >> 16);
+                    ex.w = o * 0x10001u + (r1.w << 16); o += (r1.w & 0xFFFFu) + (r1.w >> 16);
+                    ((uint4*)myscr)[1] = ex;
+                    T0 = o;
+                }
+                const u32 pos = cnt;
+                const bool bad = pos >= 255u || T0 + 2 * pos >= limit;
+                if (!bad) {
+                    const u32 c0 = P[s], c1 = s < 15 ? (u32)P[s + 1] : T0;
+                    const u32 kk = s >> 2, sh = (s & 3u) * 8;
+                    const u32 vk = kk == 0 ? v[0] : kk == 1 ? v[1] : kk == 2 ? v[2] : v[3];
+                    const u32 nf = (vk >> sh) & 255u;
+                    u32 nc = bytesum(vk & ((1u << sh) - 1u));
+                    nc += kk > 0 ? bytesum(v[0]) : 0u; nc += kk > 1 ? bytesum(v[1]) : 0u; nc += kk > 2 ? bytesum(v[2]) : 0u;
+                    S.x.trip[e & (TT - 1)] = TRIP(c1 - c0 + 2 * nf, c0 + 2 * nc, T0 + 2 * pos);
+                } else {
+                    badmask |= 1u << j;
+                    if (pos == 0 || !(pos - 1 >= 255u || T0 + 2 * (pos - 1) >= limit)) S.longs[atomicAdd(&S.n_long, 1u)] = (u16)(p0 + j - pos);
+                }
+            }
+            cnt_add(v, s); ++cnt;
+        }
+    }
+    __syncthreads();
+    // P3: the last member of every run the scan covered adds the run's counts to the row
+    v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; v[3] = c[3];
+    tails &= ~badmask & ((1u << nval) - 1u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if ((heads >> j) & 1u) { v[0] = v[1] = v[2] = v[3] = 0u; }
+        cnt_add(v, (sy >> (4 * j)) & 15u);
+        if ((tails >> j) & 1u) {
+            const u32 k = sorted[p0 + j] >> TT_SHIFT;
+            uint4* rowp = (uint4*)(tab + (u64)k * 32);
+            uint4 r0 = rowp[0], r1 = rowp[1];
+            if ((r0.x & 0xFFFFu) == 0) {
+                r0 = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u); r1 = r0;
+                touched[atomicAdd(&S.n_touched, 1u)] = k;
+            }
+            // byte counters -> 16-bit lanes, doubled
+            r0.x += 2 * __byte_perm(v[0], 0u, 0x4140); r0.y += 2 * __byte_perm(v[0], 0u, 0x4342);
+            r0.z += 2 * __byte_perm(v[1], 0u, 0x4140); r0.w += 2 * __byte_perm(v[1], 0u, 0x4342);
+            r1.x += 2 * __byte_perm(v[2], 0u, 0x4140); r1.y += 2 * __byte_perm(v[2], 0u, 0x4342);
+            r1.z += 2 * __byte_perm(v[3], 0u, 0x4140); r1.w += 2 * __byte_perm(v[3], 0u, 0x4342);
+            rowp[0] = r0; rowp[1] = r1;
+        }
+    }
+}
+
 // F: FetchQ / FetchD (rc_model.cu). scratch: per-CTA global scratch for the touched-context list (M entries).
 template <int N, class F>
 __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8* tab, u32* touched, u64* trip,
@@ -251,6 +405,7 @@ __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8
         const u32 n = min((u32)TT, M - t0);
         __syncthreads();
         if (tid == 0) { S.n_heads[0] = S.n_heads[1] = S.n_heads[2] = 0; S.n_long = 0; }
+        f.prefetch(t0 + TT, tid);                    // next tile's input towards L2 while this one is processed
         // contexts of the tile, in original order
         {
             const u32 wb = w * (TT / DSRC_WARPS);
@@ -271,35 +426,42 @@ __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8
         for (u32 ps = 0; ps < passes; ++ps) { tile_sort_pass(S, scan, S.el[cur], S.el[cur ^ 1], n, TT_SHIFT + ps * pbits, pbits); cur ^= 1; }
         const u32* sorted = S.el[cur];
         PROF_MARK(pb + 1);
-        // group heads, by size class
-        for (u32 p0 = 0; p0 < n; p0 += DSRC_CTA) {
-            const u32 p = p0 + tid; const bool in = p < n;
-            const u32 key = in ? sorted[p] >> TT_SHIFT : 0u;
-            int cls = -1;
-            if (in && (p == 0 || (sorted[p - 1] >> TT_SHIFT) != key)) {
-                if (!(p + 2 < n && (sorted[p + 2] >> TT_SHIFT) == key)) cls = 0;
-                else if (!(p + TAB_C1 < n && (sorted[p + TAB_C1] >> TT_SHIFT) == key)) cls = 1;
-                else if (!(p + TAB_LONG < n && (sorted[p + TAB_LONG] >> TT_SHIFT) == key)) cls = 2;
-                else S.longs[atomicAdd(&S.n_long, 1u)] = (u16)p;
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const u32 m = __ballot_sync(FULL, cls == c);
-                if (m) {
-                    u32 base = 0;
-                    const int leader = __ffs(m) - 1;
-                    if ((int)ln == leader) base = atomicAdd(&S.n_heads[c], (u32)__popc(m));
-                    base = __shfl_sync(FULL, base, leader);
-                    u16* list = c == 0 ? S.heads : c == 1 ? S.heads1 : S.heads2;
-                    if (cls == c) list[base + __popc(m & lt)] = (u16)p;
+        if (N == 16) {
+            // ---- scan engine: counts by segmented prefix sums, rows met by every element in parallel
+            tab_scan_groups16(S, sorted, S.el[cur ^ 1], n, tab, touched);
+            PROF_MARK(pb + 3);
+            tab_long_groups<N>(S, sorted, n, tab, touched);
+        } else {
+            // group heads, by size class
+            for (u32 p0 = 0; p0 < n; p0 += DSRC_CTA) {
+                const u32 p = p0 + tid; const bool in = p < n;
+                const u32 key = in ? sorted[p] >> TT_SHIFT : 0u;
+                int cls = -1;
+                if (in && (p == 0 || (sorted[p - 1] >> TT_SHIFT) != key)) {
+                    if (!(p + 2 < n && (sorted[p + 2] >> TT_SHIFT) == key)) cls = 0;
+                    else if (!(p + TAB_C1 < n && (sorted[p + TAB_C1] >> TT_SHIFT) == key)) cls = 1;
+                    else if (!(p + TAB_LONG < n && (sorted[p + TAB_LONG] >> TT_SHIFT) == key)) cls = 2;
+                    else S.longs[atomicAdd(&S.n_long, 1u)] = (u16)p;
+                }
+    #pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const u32 m = __ballot_sync(FULL, cls == c);
+                    if (m) {
+                        u32 base = 0;
+                        const int leader = __ffs(m) - 1;
+                        if ((int)ln == leader) base = atomicAdd(&S.n_heads[c], (u32)__popc(m));
+                        base = __shfl_sync(FULL, base, leader);
+                        u16* list = c == 0 ? S.heads : c == 1 ? S.heads1 : S.heads2;
+                        if (cls == c) list[base + __popc(m & lt)] = (u16)p;
+                    }
                 }
             }
+            __syncthreads();
+            PROF_MARK(pb + 2);
+            tab_short_groups<N>(S, sorted, n, tab, touched);
+            if (ws.prof) { __syncthreads(); PROF_MARK(pb + 3); }
+            tab_long_groups<N>(S, sorted, n, tab, touched);
         }
-        __syncthreads();
-        PROF_MARK(pb + 2);
-        tab_short_groups<N>(S, sorted, n, tab, touched);
-        if (ws.prof) { __syncthreads(); PROF_MARK(pb + 3); }
-        tab_long_groups<N>(S, sorted, n, tab, touched);
         __syncthreads();
         PROF_MARK(pb + 4);
         for (u32 p = tid; p < n; p += DSRC_CTA) trip[t0 + p] = S.x.trip[p];

@@ -101,6 +101,7 @@ struct FetchSorted {
     typedef u64 Raw;
     const u64* src;
     __device__ __forceinline__ void begin(u32) {}
+    __device__ __forceinline__ void prefetch(u32, u32) {}
     __device__ __forceinline__ Raw ld(u32 i, bool in) { return in ? src[i] : 0ull; }
     __device__ __forceinline__ u64 mk(Raw r, u32, bool) { return r; }
 };
@@ -113,6 +114,12 @@ struct FetchQ {
     {
         const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? rank[q[j]] : 0u;
         if (fixed_len) jpos = (start + lane_id()) % fixed_len;
+    }
+    __device__ __forceinline__ void prefetch(u32 start, u32 t)      // 2 KB of symbols (and of position buckets) = 16 lines each
+    {
+        const u32 i = start + (t & 15u) * 128;
+        if (t < 16) { if (i < M) asm volatile("prefetch.global.L2 [%0];" :: "l"(q + i)); }
+        else if (t < 32 && !fixed_len) { if (i < M) asm volatile("prefetch.global.L2 [%0];" :: "l"(pctx + i)); }
     }
     __device__ __forceinline__ Raw ld(u32 i, bool in)
     {
@@ -148,6 +155,7 @@ struct FetchD {
     typedef u32 Raw;
     const u8* sq; u32 ord, bits, M; u32 prev;
     __device__ __forceinline__ void begin(u32 start) { const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? sq[j] : 0u; }
+    __device__ __forceinline__ void prefetch(u32 start, u32 t) { const u32 i = start + t * 128; if (t < 16 && i < M) asm volatile("prefetch.global.L2 [%0];" :: "l"(sq + i)); }
     __device__ __forceinline__ Raw ld(u32 i, bool in) { return in ? sq[i] : 0u; }
     __device__ __forceinline__ u64 mk(Raw r0, u32 i, bool in)
     {
