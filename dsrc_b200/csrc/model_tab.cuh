@@ -286,7 +286,7 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
 
     // P1: aggregate of this thread's 8 elements (counts since the last run head inside the thread, or of all 8)
     u32 v[4] = {0u, 0u, 0u, 0u}, cnt = 0, flag = heads ? 1u : 0u;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 8; ++j) {
         if ((heads >> j) & 1u) { v[0] = v[1] = v[2] = v[3] = 0u; cnt = 0; }
         cnt_add(v, (sy >> (4 * j)) & 15u); ++cnt;
@@ -319,13 +319,13 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
     }
 
     // P2: every element meets its row
-    u32 badmask = 0;
+    u32 badmask = 0, freshmask = 0;
     {
-        u32 T0 = 0;
+        u32 T0 = 0; bool fresh = false;
         u32* const myscr = scratch + tid * 8;        // exclusive prefix sums of the current row, 16 x u16
         const u16* P = (const u16*)myscr;
         v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; v[3] = c[3]; cnt = ccnt;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 8; ++j) {
             const u32 s = (sy >> (4 * j)) & 15u;
             const bool head = (heads >> j) & 1u;
@@ -335,7 +335,8 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
                 if (j == 0 || head) {
                     const uint4* rowp = (const uint4*)(tab + (u64)(e >> TT_SHIFT) * 32);
                     uint4 r0 = rowp[0], r1 = rowp[1];
-                    if ((r0.x & 0xFFFFu) == 0) { r0 = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u); r1 = r0; }
+                    fresh = (r0.x & 0xFFFFu) == 0;
+                    if (fresh) { r0 = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u); r1 = r0; }
                     u32 o = 0; uint4 ex;
                     ex.x = o * 0x10001u + (r0.x << 16); o += (r0.x & 0xFFFFu) + (r0.x >> 16);
                     ex.y = o * 0x10001u + (r0.y << 16); o += (r0.y & 0xFFFFu) + (r0.y >> 16);
@@ -351,6 +352,7 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
                 }
                 const u32 pos = cnt;
                 const bool bad = pos >= 255u || T0 + 2 * pos >= limit;
+                freshmask |= (fresh ? 1u : 0u) << j;
                 if (!bad) {
                     const u32 c0 = P[s], c1 = s < 15 ? (u32)P[s + 1] : T0;
                     const u32 kk = s >> 2, sh = (s & 3u) * 8;
@@ -368,27 +370,33 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
         }
     }
     __syncthreads();
-    // P3: the last member of every run the scan covered adds the run's counts to the row
+    // P3: the last member of every run the scan covered adds the run's counts to the row -- without reading it again: a row
+    // that was fresh is stored whole (ones + counts), any other receives its non-zero words as fire-and-forget reductions
     v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; v[3] = c[3];
     tails &= ~badmask & ((1u << nval) - 1u);
+    if (tails) {
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            if ((heads >> j) & 1u) { v[0] = v[1] = v[2] = v[3] = 0u; }
+            cnt_add(v, (sy >> (4 * j)) & 15u);
+            if ((tails >> j) & 1u) {
+                const u32 k = sorted[p0 + j] >> TT_SHIFT;
+                u32* rowp = (u32*)(tab + (u64)k * 32);
+                // byte counters -> 16-bit lanes, doubled
+                u32 d[8];
+                d[0] = 2 * __byte_perm(v[0], 0u, 0x4140); d[1] = 2 * __byte_perm(v[0], 0u, 0x4342);
+                d[2] = 2 * __byte_perm(v[1], 0u, 0x4140); d[3] = 2 * __byte_perm(v[1], 0u, 0x4342);
+                d[4] = 2 * __byte_perm(v[2], 0u, 0x4140); d[5] = 2 * __byte_perm(v[2], 0u, 0x4342);
+                d[6] = 2 * __byte_perm(v[3], 0u, 0x4140); d[7] = 2 * __byte_perm(v[3], 0u, 0x4342);
+                if ((freshmask >> j) & 1u) {
+                    touched[atomicAdd(&S.n_touched, 1u)] = k;
+                    ((uint4*)rowp)[0] = make_uint4(d[0] + 0x00010001u, d[1] + 0x00010001u, d[2] + 0x00010001u, d[3] + 0x00010001u);
+                    ((uint4*)rowp)[1] = make_uint4(d[4] + 0x00010001u, d[5] + 0x00010001u, d[6] + 0x00010001u, d[7] + 0x00010001u);
+                } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if ((heads >> j) & 1u) { v[0] = v[1] = v[2] = v[3] = 0u; }
-        cnt_add(v, (sy >> (4 * j)) & 15u);
-        if ((tails >> j) & 1u) {
-            const u32 k = sorted[p0 + j] >> TT_SHIFT;
-            uint4* rowp = (uint4*)(tab + (u64)k * 32);
-            uint4 r0 = rowp[0], r1 = rowp[1];
-            if ((r0.x & 0xFFFFu) == 0) {
-                r0 = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u); r1 = r0;
-                touched[atomicAdd(&S.n_touched, 1u)] = k;
+                    for (int q = 0; q < 8; ++q) if (d[q]) atomicAdd(&rowp[q], d[q]);
+                }
             }
-            // byte counters -> 16-bit lanes, doubled
-            r0.x += 2 * __byte_perm(v[0], 0u, 0x4140); r0.y += 2 * __byte_perm(v[0], 0u, 0x4342);
-            r0.z += 2 * __byte_perm(v[1], 0u, 0x4140); r0.w += 2 * __byte_perm(v[1], 0u, 0x4342);
-            r1.x += 2 * __byte_perm(v[2], 0u, 0x4140); r1.y += 2 * __byte_perm(v[2], 0u, 0x4342);
-            r1.z += 2 * __byte_perm(v[3], 0u, 0x4140); r1.w += 2 * __byte_perm(v[3], 0u, 0x4342);
-            rowp[0] = r0; rowp[1] = r1;
         }
     }
 }
