@@ -415,6 +415,8 @@ __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8
         if (tid == 0) { S.n_heads[0] = S.n_heads[1] = S.n_heads[2] = 0; S.n_long = 0; }
         f.prefetch(t0 + TT, tid);                    // next tile's input towards L2 while this one is processed
         // contexts of the tile, in original order
+        if (F::TILE8) f.tile8(S, t0, n);             // 8 consecutive symbols per thread, history in registers (FetchQ, 16-symbol rows)
+        else
         {
             const u32 wb = w * (TT / DSRC_WARPS);
             f.begin(t0 + wb);

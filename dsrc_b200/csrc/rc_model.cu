@@ -97,8 +97,11 @@ struct ModelShared {
 
 // ---- element sources of a sort pass. An element is (ctx << 40) | (sym << 32) | index. A warp walks consecutive rows of
 // 32 symbols; the symbols a context needs from before the row come from the neighbouring lanes / the previous row.
+struct TabShared;
 struct FetchSorted {
     typedef u64 Raw;
+    static const bool TILE8 = false;
+    __device__ __forceinline__ void tile8(TabShared&, u32, u32) {}
     const u64* src;
     __device__ __forceinline__ void begin(u32) {}
     __device__ __forceinline__ void prefetch(u32, u32) {}
@@ -108,6 +111,8 @@ struct FetchSorted {
 // quality context (TQualityModelBase::UpdateHash/GetHash, QualityEncoder.h:77-94; position bucket :307)
 struct FetchQ {
     typedef u32 Raw;
+    static const bool TILE8 = true;
+    __device__ __forceinline__ void tile8(TabShared& S, u32 t0, u32 n);
     const u8* q; const u8* pctx; const u8* rank; u32 so, h, bits, M; u32 prev;
     const u8* plut; u32 fixed_len, jpos;              // fixed_len != 0: position bucket from the shared-memory table, indexed by i % len
     __device__ __forceinline__ void begin(u32 start)
@@ -153,6 +158,8 @@ struct FetchQ {
 // DNA context: the previous `ord` symbols (TDnaRCOrderModeler, DnaModelerRCO.h:45-62)
 struct FetchD {
     typedef u32 Raw;
+    static const bool TILE8 = false;
+    __device__ __forceinline__ void tile8(TabShared&, u32, u32) {}
     const u8* sq; u32 ord, bits, M; u32 prev;
     __device__ __forceinline__ void begin(u32 start) { const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? sq[j] : 0u; }
     __device__ __forceinline__ void prefetch(u32 start, u32 t) { const u32 i = start + t * 128; if (t < 16 && i < M) asm volatile("prefetch.global.L2 [%0];" :: "l"(sq + i)); }
@@ -170,6 +177,40 @@ struct FetchD {
         return in ? (((u64)ctx << 40) | ((u64)r0 << 32) | i) : 0ull;
     }
 };
+
+// Contexts of one tile of the tile/table engine for 16-symbol quality rows (bits == 4): every thread takes 8 consecutive
+// symbols, the 5 symbols of history they need come with one more 8-byte load, so the hash window slides through registers
+// (no shuffles, two loads per thread). Same arithmetic as FetchQ::mk.
+__device__ __forceinline__ void FetchQ::tile8(TabShared& S, u32 t0, u32 n)
+{
+    const u32 p = threadIdx.x * 8, i = t0 + p;
+    if (p >= n) return;
+    const u64 cur = *(const u64*)(q + i);            // the arena has slack behind M
+    const u64 prv = i ? *(const u64*)(q + i - 8) : 0ull;
+    u32 r[13];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r[k] = i ? (u32)rank[(u32)(prv >> (8 * (3 + k))) & 255u] : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[5 + k] = rank[(u32)(cur >> (8 * k)) & 255u];
+    u64 pcw = 0; u32 jp = 0;
+    if (fixed_len) jp = i % fixed_len; else pcw = *(const u64*)(pctx + i);
+    u32 el[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        u32 pc;
+        if (fixed_len) { pc = plut[jp]; jp = jp + 1 == fixed_len ? 0u : jp + 1; } else pc = (u32)(pcw >> (8 * k)) & 255u;
+        u32 hash = 0;                                 // y[t] = r[5 + k - t]: symbol t steps back
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if ((u32)t < so) {
+            const u32 v = (u32)t < h ? r[4 + k - t] : ((r[4 + k - t] + r[3 + k - t]) >> 1);
+            hash |= v << (t * 4);
+        }
+        el[k] = ((((hash << 4) | pc)) << TT_SHIFT) | (p + k);
+    }
+    ((uint4*)S.el[0])[threadIdx.x * 2] = make_uint4(el[0], el[1], el[2], el[3]);
+    ((uint4*)S.el[0])[threadIdx.x * 2 + 1] = make_uint4(el[4], el[5], el[6], el[7]);
+    *(uint2*)&S.sym[p] = make_uint2(r[5] | (r[6] << 8) | (r[7] << 16) | (r[8] << 24), r[9] | (r[10] << 8) | (r[11] << 16) | (r[12] << 24));
+}
 
 // One stable counting-sort pass on the `bits`-wide digit at `shift`. Every warp owns a contiguous eighth of the input:
 // it histograms its part into its own counters, the counters are scanned in (digit, warp) order, and each warp
