@@ -115,6 +115,7 @@ struct FetchQ {
     __device__ __forceinline__ void tile8(TabShared& S, u32 t0, u32 n);
     const u8* q; const u8* pctx; const u8* rank; u32 so, h, bits, M; u32 prev;
     const u8* plut; u32 fixed_len, jpos;              // fixed_len != 0: position bucket from the shared-memory table, indexed by i % len
+    u32 ebits, pbits;                                 // tile8: bits per hash slot / per position bucket of the compact row index
     __device__ __forceinline__ void begin(u32 start)
     {
         const u32 j = start - 32 + lane_id(); prev = (start >= 32 && j < M) ? rank[q[j]] : 0u;
@@ -180,7 +181,10 @@ struct FetchD {
 
 // Contexts of one tile of the tile/table engine for 16-symbol quality rows (bits == 4): every thread takes 8 consecutive
 // symbols, the 5 symbols of history they need come with one more 8-byte load, so the hash window slides through registers
-// (no shuffles, two loads per thread). Same arithmetic as FetchQ::mk.
+// (no shuffles, two loads per thread). Same arithmetic as FetchQ::mk, except that the row index is packed with as many
+// bits per hash slot as the block's symbol count needs (symbols are dense ranks, their pairwise means are no larger) and
+// log2(rescale) bits of position bucket: the index only has to be injective -- the table is private to the block -- and a
+// 5-symbol block then sorts 16-bit keys (two 8-bit passes, 256 bins) instead of 20-bit ones and keeps its rows within 2 MB.
 __device__ __forceinline__ void FetchQ::tile8(TabShared& S, u32 t0, u32 n)
 {
     const u32 p = threadIdx.x * 8, i = t0 + p;
@@ -203,9 +207,9 @@ __device__ __forceinline__ void FetchQ::tile8(TabShared& S, u32 t0, u32 n)
 #pragma unroll
         for (int t = 0; t < 4; ++t) if ((u32)t < so) {
             const u32 v = (u32)t < h ? r[4 + k - t] : ((r[4 + k - t] + r[3 + k - t]) >> 1);
-            hash |= v << (t * 4);
+            hash |= v << (t * ebits);
         }
-        el[k] = ((((hash << 4) | pc)) << TT_SHIFT) | (p + k);
+        el[k] = ((((hash << pbits) | pc)) << TT_SHIFT) | (p + k);
     }
     ((uint4*)S.el[0])[threadIdx.x * 2] = make_uint4(el[0], el[1], el[2], el[3]);
     ((uint4*)S.el[0])[threadIdx.x * 2 + 1] = make_uint4(el[4], el[5], el[6], el[7]);
@@ -523,7 +527,9 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_s
             }
             if (QUALITY) {
                 FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M; f.plut = TS.plut; f.fixed_len = fixed_len; f.jpos = 0;
-                tab_engine<16>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 16);
+                f.ebits = 1; while ((1u << f.ebits) < st.q_count) ++f.ebits;
+                f.pbits = cfg.rescale > 8 ? 4 : 3;
+                tab_engine<16>(TS, S.scan, f, M, f.pbits + cfg.sym_order * f.ebits, tab, (u32*)bufA, trip, ws, prof_t, 16);
             } else {
                 FetchD f; f.sq = ws.dcat + d.sym_base; f.ord = cfg.ord; f.bits = cfg.bits; f.prev = 0; f.M = M;
                 if (cfg.alpha == 4) tab_engine<4>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 24);
