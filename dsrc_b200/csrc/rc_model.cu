@@ -20,6 +20,9 @@
 #include "kernels.h"
 #include <cstddef>
 
+#ifndef MODEL_REGS
+#define MODEL_REGS 56
+#endif
 #define SORT_MAX_BITS 10                      // radix digits of at most 10 bits: 8 warps x 1024 counters = 32 KB
 #define LONG_T 48                             // context runs longer than this are walked by a whole warp
 #define SCAN_TILE 2048                        // sorted elements staged in shared memory per step of the run walker
@@ -440,7 +443,7 @@ __device__ u32 tab_acquire(u32* mask, u32 count)
 __device__ void tab_release(u32* mask, u32 id) { atomicAnd(&mask[id >> 5], ~(1u << (id & 31))); }
 
 template <bool QUALITY>
-__global__ void __launch_bounds__(DSRC_CTA, 4) k_model(Workspace ws, u64 arena_stride)
+__global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 {
     extern __shared__ __align__(16) u8 model_smem[];       // sizeof(ModelShared) > 48 KiB: opt-in dynamic shared memory
     ModelShared& S = *(ModelShared*)model_smem;
