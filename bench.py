@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-serial", action="store_true", help="skip the extra single-slot pass that isolates per-kernel durations")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -359,9 +360,38 @@ def main():
     sampler.stop = True
     sampler.join(timeout=2)
 
-    # roofline of the dominant kernel (CUDA-event time inside the timed steps)
+    # one more pass of the same step with a single batch in flight: with several slots the CUDA-event pairs of a kernel include the
+    # time it shares the SMs with (or waits for) the other slots' kernels, so the roofline below uses these isolated durations
+    kser = None
+    if not args.no_serial:
+        L.dsrcgpu_release_workspace(ctx)
+        old = os.environ.get("DSRCGPU_SLOTS")
+        os.environ["DSRCGPU_SLOTS"] = "1"
+        ctx1 = C.c_void_p()
+        rc = L.dsrcgpu_create(C.byref(ctx1), local_rank, C.byref(ds), C.byref(cs), BLOCK_BYTES, args.inflight)
+        if old is None:
+            del os.environ["DSRCGPU_SLOTS"]
+        else:
+            os.environ["DSRCGPU_SLOTS"] = old
+        if rc == 0:
+            ssz = np.zeros(n, dtype=np.uint32)
+            for _ in range(2):
+                rc1 = L.dsrcgpu_encode_blocks_device(ctx1, C.c_void_p(d_in.data_ptr()), offs.ctypes.data_as(_lib.u64p), lens.ctypes.data_as(_lib.u32p),
+                                                     None, n, C.c_void_p(d_out.data_ptr()), out_cap, ssz.ctypes.data_as(_lib.u32p), None, None)
+            if rc1 == 0 and bool((ssz == sizes).all()):
+                names = (C.c_char_p * 16)()
+                ms = (C.c_float * 16)()
+                ln = (C.c_uint32 * 16)()
+                k = L.dsrcgpu_last_kernel_times(ctx1, names, ms, ln, 16)
+                kser = {names[i].decode(): (float(ms[i]), int(ln[i])) for i in range(k)}
+                kser["_step_ms"] = (float(L.dsrcgpu_last_call_ms(ctx1)), 1)
+            L.dsrcgpu_destroy(ctx1)
+
+    # roofline of the dominant kernel (CUDA-event time of its launches; isolated durations when the serialised pass ran)
     peak, peak_kind = load_peaks()
-    dom = max(ktot.items(), key=lambda kv: kv[1][0]) if ktot else ("none", (0.0, 0))
+    ser_step_ms = kser.pop("_step_ms")[0] if kser else None
+    kbase = {k: (v[0] * args.steps, v[1] * args.steps) for k, v in kser.items()} if kser else ktot
+    dom = max(kbase.items(), key=lambda kv: kv[1][0]) if kbase else ("none", (0.0, 0))
     syms = n_reads * 150
     alg = {   # algorithmic bytes per step of each kernel family (DESIGN.md "kernels"): what the kernel must read + write
         "count_lines": payload, "parse": payload, "preprocess": payload + 2 * syms,
@@ -387,8 +417,13 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg.get(dom[0], 0) / max(1, dom[1][1] // max(1, args.steps)),
-                "note": "kernel times are CUDA-event pairs on the launching stream; with 3 batches in flight they include time shared with other streams' kernels",
+                "note": "achieved = algorithmic bytes / CUDA-event time of the kernel's launches in one extra pass of the same step with a single batch "
+                        "in flight (kernel_ms_serialized); kernel_ms_per_step are the event pairs inside the timed steps, where 3 batches are in flight "
+                        "and a kernel's pair includes time shared with the other streams' kernels" if kser else
+                        "kernel times are CUDA-event pairs on the launching stream; with 3 batches in flight they include time shared with other streams' kernels",
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktot.items()},
+                "kernel_ms_serialized": {k: v[0] for k, v in kser.items()} if kser else None,
+                "serialized_step_ms": ser_step_ms,
                 "launches_per_kernel_per_step": max(1, dom[1][1] // max(1, args.steps)),
                 "block_path_compulsory_frac": (payload + comp_bytes) / step_s / 1e9 / peak,
                 "block_path_survey_A_frac": (payload + comp_bytes + syms * 64) / step_s / 1e9 / peak}

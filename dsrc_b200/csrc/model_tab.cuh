@@ -56,10 +56,28 @@ __device__ __forceinline__ void tile_sort_pass_t(TabShared& S, u32* scan, const 
     u32* H32 = (u32*)H;
     for (u32 i = tid; i < DSRC_WARPS * bins / 2; i += DSRC_CTA) ((u32*)S.x.H)[i] = 0;
     __syncthreads();
-    // per-warp digit histogram: packed 16-bit counters bumped with 32-bit shared atomics (counts <= 256, no carry)
-    for (u32 r = wb; r < we; r += 32) {
-        const u32 i = r + ln;
-        if (i < we) { const u32 d = (src[i] >> shift) & dmask; atomicAdd(&H32[d >> 1], 1u << ((d & 1) * 16)); }
+    // the warp's 8 rows of 32 elements: element, and the lanes of its row holding the same digit -- found once, used by the
+    // histogram (one shared reduction per distinct digit of a row: packed 16-bit counters, counts <= 256, no carry) and, after
+    // the scan, by the scatter
+    constexpr int ROWS = TT / DSRC_WARPS / 32;
+    u32 e[ROWS], peers[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) { const u32 i = wb + 32 * k + ln; e[k] = i < we ? src[i] : 0u; }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+        const bool in = wb + 32 * k + ln < we;
+        const u32 d = (e[k] >> shift) & dmask;
+        u32 p = __ballot_sync(FULL, in);
+#if TAB_MATCH_ANY
+        if (BITS >= TAB_MATCH_ANY) { if (in) p = __match_any_sync(p, d); }
+        else
+#endif
+        {
+#pragma unroll
+            for (int q = 0; q < BITS; ++q) { const u32 m = __ballot_sync(FULL, (d >> q) & 1u); p &= ((d >> q) & 1u) ? m : ~m; }
+        }
+        peers[k] = in ? p : 0u;
+        if (in && (__ffs(p) - 1) == (int)ln) atomicAdd(&H32[d >> 1], (u32)__popc(p) << ((d & 1) * 16));
     }
     __syncthreads();
     {
@@ -70,24 +88,14 @@ __device__ __forceinline__ void tile_sort_pass_t(TabShared& S, u32* scan, const 
         if (d0 < bins) for (u32 k = 0; k < per; ++k) for (u32 ww = 0; ww < DSRC_WARPS; ++ww) { const u32 c = S.x.H[ww * bins + d0 + k]; S.x.H[ww * bins + d0 + k] = (u16)run; run += c; }
     }
     __syncthreads();
-    for (u32 r = wb; r < we; r += 32) {
-        const u32 i = r + ln; const bool in = i < we;
-        const u32 e = in ? src[i] : 0u;
-        const u32 d = (e >> shift) & dmask;
-        u32 peers = __ballot_sync(FULL, in);
-#if TAB_MATCH_ANY
-        if (BITS >= TAB_MATCH_ANY) { if (in) peers = __match_any_sync(peers, d); }
-        else
-#endif
-        {
 #pragma unroll
-        for (int k = 0; k < BITS; ++k) { const u32 m = __ballot_sync(FULL, (d >> k) & 1u); peers &= ((d >> k) & 1u) ? m : ~m; }
-        }
-        const u32 pos = in ? H[d] + __popc(peers & lt) : 0u;
+    for (int k = 0; k < ROWS; ++k) {
+        const u32 p = peers[k], d = (e[k] >> shift) & dmask;
+        const u32 pos = p ? H[d] + __popc(p & lt) : 0u;
         __syncwarp();
-        if (in) {
-            if ((__ffs(peers) - 1) == (int)ln) H[d] += (u16)__popc(peers);
-            dst[pos] = e;
+        if (p) {
+            if ((__ffs(p) - 1) == (int)ln) H[d] += (u16)__popc(p);
+            dst[pos] = e[k];
         }
         __syncwarp();
     }

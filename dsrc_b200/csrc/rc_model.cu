@@ -568,6 +568,13 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 // and, for quality, the 256-bit symbol mask of TTranslationalQualityEncoder::Store (QualityEncoder.h:332-342).
 // ------------------------------------------------------------------------------------------------
 #define RC_CTA 64
+// the carry-less range adjustment of RangeEncoder::EncodeFrequency (src/RangeCoder.h:66-70); out of line: it is reached
+// about once per 2^24 output bytes (see RC_STEP) and must not cost the common path any predicated instructions
+__device__ __noinline__ u32 rc_carry_fix(u64 low, u32 range)
+{
+    if ((u32)((low ^ (low + range)) >> 56)) range = ~(u32)low & 0x00FFFFFFu;   // (r | 0xFFFFFF) - r
+    return range;
+}
 #ifndef RC_RING
 #define RC_RING 6
 #endif
@@ -622,7 +629,9 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(Workspace ws, u32 do_q
         u32 q_ = __umulhi(range, (m)); q_ += (range - q_ * tot_ >= tot_) ? 1u : 0u; \
         low += (u64)(q_ * cum_); range = q_ * f_; \
         while (range <= 0x00FFFFFFu) { \
-            if ((u32)((low ^ (low + range)) >> 56)) range = ~(u32)low & 0x00FFFFFFu;   /* (r | 0xFFFFFF) - r */ \
+            /* (low ^ (low + range)) & 0xFF00..: range < 2^24 reaches the top byte only through a carry across bits 32..55, */ \
+            /* i.e. only if they are all ones -- tested first, the full test behind it is almost never evaluated */ \
+            if ((((u32)(low >> 32)) | 0xFF000000u) == 0xFFFFFFFFu) range = rc_carry_fix(low, range); \
             RC_PUT_TOP(); low <<= 8; range <<= 8; \
         } } while (0)
 #define RC_RCP(tr) __ldg(&g_rcp_lut[(u32)((tr) >> 32) & 0xFFFFu])
