@@ -301,8 +301,8 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     CK(sl.streams.ensure(streams));
     if (rc_q || rc_d) { CK(sl.elem_a.ensure(ctx->model_stride * 8 * ctx->model_ctas)); CK(sl.elem_b.ensure(ctx->model_stride * 8 * ctx->model_ctas)); }
     if ((rc_q || rc_d) && !ctx->tab.p && ctx->tab_stride) {
-        // one table per model CTA that can be resident at a time (4 per SM, the kernels' launch bound), whatever the slot
-        ctx->tab_count = (u32)std::max<u64>(1, std::min<u64>((u64)ctx->sms * 5, (24ull << 30) / ctx->tab_stride));
+        // one table per model CTA that can be resident at a time (at most 5 per SM), whatever the slot; small contexts need fewer
+        ctx->tab_count = (u32)std::max<u64>(1, std::min<u64>(std::min<u64>((u64)ctx->sms * 5, (u64)ctx->model_ctas * ctx->n_slots), (24ull << 30) / ctx->tab_stride));
         CK(ctx->tab.ensure(ctx->tab_stride * ctx->tab_count));
         CK(ctx->tab_mask.ensure(((ctx->tab_count + 31) / 32) * 4));
         CK(cudaMemsetAsync(ctx->tab.p, 0, ctx->tab.cap, s));    // invariant between blocks: first counter of every row is 0
