@@ -568,13 +568,6 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 // and, for quality, the 256-bit symbol mask of TTranslationalQualityEncoder::Store (QualityEncoder.h:332-342).
 // ------------------------------------------------------------------------------------------------
 #define RC_CTA 64
-// the carry-less range adjustment of RangeEncoder::EncodeFrequency (src/RangeCoder.h:66-70); out of line: it is reached
-// about once per 2^24 output bytes (see RC_STEP) and must not cost the common path any predicated instructions
-__device__ __noinline__ u32 rc_carry_fix(u64 low, u32 range)
-{
-    if ((u32)((low ^ (low + range)) >> 56)) range = ~(u32)low & 0x00FFFFFFu;   // (r | 0xFFFFFF) - r
-    return range;
-}
 #ifndef RC_RING
 #define RC_RING 6
 #endif
@@ -624,45 +617,62 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(Workspace ws, u32 do_q
         pos += on;
     }
 #define RC_PUT_TOP() do { obuf = __byte_perm(obuf, (u32)(low >> 32), 0x7321); ++pos; if ((pos & 3u) == 0) *(u32*)(out + pos - 4) = obuf; } while (0)
-#define RC_STEP(tr, m) do { \
-        const u32 f_ = (u32)(tr) & 0xFFFFu, cum_ = (u32)(tr) >> 16, tot_ = (u32)((tr) >> 32); \
+    // One renormalisation step of RangeEncoder::EncodeFrequency (src/RangeCoder.h:62-72), written WITHOUT a branch: the chain puts
+    // a byte out iff range <= 2^24 - 1, everything is predicated on that. Divergent branches are what a lone warp of chains
+    // pays most for (ncu: BSSY/BRA/BSYNC held half of the stall samples of the looped form), and at warp level some lane needs
+    // a byte in 98 % of the steps anyway. The carry-less adjustment `(low ^ (low + range)) & 0xFF00..` can only be non-zero if
+    // low + range carries out of the low word AND bits 32..55 of low are all ones.
+#define RC_RENORM() do { \
+        const bool n_ = range <= 0x00FFFFFFu; \
+        const u32 lo_ = (u32)low, hi_ = (u32)(low >> 32); \
+        const bool cy_ = n_ && (lo_ + range < lo_) && ((hi_ & 0x00FFFFFFu) == 0x00FFFFFFu); \
+        range = cy_ ? (~lo_ & 0x00FFFFFFu) : range;                      /* (r | 0xFFFFFF) - r */ \
+        obuf = __byte_perm(obuf, hi_, n_ ? 0x7321u : 0x3210u); \
+        pos += n_ ? 1u : 0u; \
+        if (n_ && (pos & 3u) == 0) *(u32*)(out + pos - 4) = obuf; \
+        const u32 sh_ = n_ ? 8u : 0u; low <<= sh_; range <<= sh_; } while (0)
+#define RC_STEP(lo_w, hi_w, m) do { \
+        const u32 f_ = (lo_w) & 0xFFFFu, cum_ = (lo_w) >> 16, tot_ = (hi_w); \
         u32 q_ = __umulhi(range, (m)); q_ += (range - q_ * tot_ >= tot_) ? 1u : 0u; \
         low += (u64)(q_ * cum_); range = q_ * f_; \
-        while (range <= 0x00FFFFFFu) { \
-            /* (low ^ (low + range)) & 0xFF00..: range < 2^24 reaches the top byte only through a carry across bits 32..55, */ \
-            /* i.e. only if they are all ones -- tested first, the full test behind it is almost never evaluated */ \
-            if ((((u32)(low >> 32)) | 0xFF000000u) == 0xFFFFFFFFu) range = rc_carry_fix(low, range); \
-            RC_PUT_TOP(); low <<= 8; range <<= 8; \
-        } } while (0)
-#define RC_RCP(tr) __ldg(&g_rcp_lut[(u32)((tr) >> 32) & 0xFFFFu])
+        RC_RENORM();                                                     /* the first byte, if any: no branch */ \
+        while (range <= 0x00FFFFFFu) RC_RENORM();                        /* a second byte in one step is rare */ \
+    } while (0)
+#define RC_RCP(hi_) __ldg(&g_rcp_lut[(hi_)])      /* hi word of a triple the model kernels wrote = tot < 2^16 */
     __shared__ __align__(16) ulonglong2 ring[RC_RING][2][RC_CTA];       // [slot][half][thread]: conflict-free 16-byte cells
-    const u32 tx = threadIdx.x;
-    auto fetch = [&](u32 g) {                                          // sector g of this chain -> ring slot g % RC_RING (cp.async, L2 only)
-        if (g < G) {
-            const u32 sl = g % RC_RING;
-            const u32 a0 = (u32)__cvta_generic_to_shared(&ring[sl][0][tx]), a1 = (u32)__cvta_generic_to_shared(&ring[sl][1][tx]);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(a0), "l"(trip + 2 * g) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(a1), "l"(trip + 2 * g + 1) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");           // one group per sector, empty past the end: uniform counting
-    };
-    for (u32 k = 0; k < RC_RING; ++k) fetch(k);
+    constexpr u32 SLOT = 2 * RC_CTA * 16, HALF = RC_CTA * 16;          // bytes per ring slot / per half slot
+    const u32 rb = (u32)__cvta_generic_to_shared(&ring[0][0][threadIdx.x]);
+    const u8* const rp = (const u8*)&ring[0][0][threadIdx.x];
+    // sector g of this chain -> ring slot at byte offset `so` (cp.async, L2 only); one group per call, empty past the end, so the
+    // group counting of wait_group is uniform
+#define RC_FETCH(g, so) do { \
+        if ((g) < G) { \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rb + (so)), "l"(trip + 2 * (g)) : "memory"); \
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rb + (so) + HALF), "l"(trip + 2 * (g) + 1) : "memory"); \
+        } \
+        asm volatile("cp.async.commit_group;" ::: "memory"); } while (0)
+#pragma unroll
+    for (u32 k = 0; k < RC_RING; ++k) RC_FETCH(k, k * SLOT);
     asm volatile("cp.async.wait_group %0;" :: "n"(RC_RING - 1) : "memory");
     u32 mn0 = 0, mn1 = 0, mn2 = 0, mn3 = 0;
-    if (G) { const ulonglong2 n0 = ring[0][0][tx], n1 = ring[0][1][tx]; mn0 = RC_RCP(n0.x); mn1 = RC_RCP(n0.y); mn2 = RC_RCP(n1.x); mn3 = RC_RCP(n1.y); }
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;                        // the next sector's 4 triples, (lo, hi) word pairs, one sector ahead in registers
+    if (G) { n0 = *(const uint4*)rp; n1 = *(const uint4*)(rp + HALF); mn0 = RC_RCP(n0.y); mn1 = RC_RCP(n0.w); mn2 = RC_RCP(n1.y); mn3 = RC_RCP(n1.w); }
+    u32 so = 0;                                                        // byte offset of the ring slot of sector g
     for (u32 g = 0; g < G; ++g) {
-        const u32 sl = g % RC_RING, sn = (g + 1) % RC_RING;
-        const ulonglong2 c0 = ring[sl][0][tx], c1 = ring[sl][1][tx];
+        const u32 sn = so + SLOT == RC_RING * SLOT ? 0u : so + SLOT;
+        const uint4 c0 = n0, c1 = n1;
         const u32 m0 = mn0, m1 = mn1, m2 = mn2, m3 = mn3;
         asm volatile("cp.async.wait_group %0;" :: "n"(RC_RING - 2) : "memory");      // sector g+1 has landed
-        if (g + 1 < G) {   // reciprocals of the next sector's totals: in flight while this sector is coded
-            const ulonglong2 n0 = ring[sn][0][tx], n1 = ring[sn][1][tx];
-            mn0 = RC_RCP(n0.x); mn1 = RC_RCP(n0.y); mn2 = RC_RCP(n1.x); mn3 = RC_RCP(n1.y);
+        if (g + 1 < G) {   // next sector and the reciprocals of its totals: in flight while this sector is coded
+            n0 = *(const uint4*)(rp + sn); n1 = *(const uint4*)(rp + sn + HALF);
+            mn0 = RC_RCP(n0.y); mn1 = RC_RCP(n0.w); mn2 = RC_RCP(n1.y); mn3 = RC_RCP(n1.w);
         }
-        fetch(g + RC_RING);                                            // refills the slot just read
-        RC_STEP(c0.x, m0); RC_STEP(c0.y, m1); RC_STEP(c1.x, m2); RC_STEP(c1.y, m3);
+        RC_FETCH(g + RC_RING, so);                                     // refills the slot of sector g (already in registers)
+        so = sn;
+        RC_STEP(c0.x, c0.y, m0); RC_STEP(c0.z, c0.w, m1); RC_STEP(c1.x, c1.y, m2); RC_STEP(c1.z, c1.w, m3);
     }
-    for (u32 i = G * 4; i < M; ++i) { const u64 tr = ((const u64*)trip)[i]; const u32 m = RC_RCP(tr); RC_STEP(tr, m); }
+#undef RC_FETCH
+    for (u32 i = G * 4; i < M; ++i) { const uint2 tr = ((const uint2*)trip)[i]; const u32 m = RC_RCP(tr.y); RC_STEP(tr.x, tr.y, m); }
     for (int k = 0; k < 8; ++k) { RC_PUT_TOP(); low <<= 8; }
     {
         const u32 on = pos & 3u;
@@ -671,6 +681,7 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(Workspace ws, u32 do_q
     st.stream_size[sidx] = pos;
 #undef RC_RCP
 #undef RC_STEP
+#undef RC_RENORM
 #undef RC_PUT_TOP
 }
 
