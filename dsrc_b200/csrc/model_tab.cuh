@@ -259,15 +259,29 @@ __device__ void tab_long_groups(TabShared& S, const u32* sorted, u32 n, u8* tab,
 // for the first 255 members of a run (a count never exceeds the member's position); a run that is longer, or that reaches
 // the rescale threshold of its row, is queued once for the warp-cooperative walker (tab_long_groups), which redoes it from its
 // head -- a few runs per block. The last member of every other run adds the run's counts to the row.
-__device__ __forceinline__ void cnt_add(u32 (&v)[4], u32 s)
+// NW = words of byte counters = live symbols / 4: the block's symbols are dense ranks < q_count, so a block with <= 8 (<= 4)
+// distinct quality values scans 2 (1) words instead of 4 and touches only the first 8 (4) counters of its rows; the dead
+// counters of a row stay at their initial 1 for ever (rescaling keeps 1 at 1) and enter `tot` as a constant.
+template <int NW> __device__ __forceinline__ void cnt_add(u32 (&v)[NW], u32 s)
 {
-    const u32 inc = 1u << ((s & 3u) * 8), k = s >> 2;
-    v[0] += k == 0 ? inc : 0u; v[1] += k == 1 ? inc : 0u; v[2] += k == 2 ? inc : 0u; v[3] += k == 3 ? inc : 0u;
+    const u32 inc = 1u << ((s & 3u) * 8);
+    if (NW == 1) v[0] += inc;
+    else {
+        const u32 k = s >> 2;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) v[q] += k == (u32)q ? inc : 0u;
+    }
+}
+template <int NW> __device__ __forceinline__ void cnt_zero(u32 (&v)[NW]) {
+#pragma unroll
+    for (int q = 0; q < NW; ++q) v[q] = 0u;
 }
 __device__ __forceinline__ u32 bytesum(u32 x) { return __vsadu4(x, 0u); }
 
+template <int NW>
 __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch, u32 n, u8* tab, u32* touched)
 {
+    constexpr u32 NS = 4 * NW, DEAD = 16 - NS;        // live symbols; counters that never move
     const u32 tid = threadIdx.x, ln = lane_id(), w = warp_id();
     const u32 limit = (1u << 16) - 32;
     const u32 p0 = tid * 8;
@@ -293,34 +307,48 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
     const u32 nval = p0 < n ? min(8u, n - p0) : 0u;
 
     // P1: aggregate of this thread's 8 elements (counts since the last run head inside the thread, or of all 8)
-    u32 v[4] = {0u, 0u, 0u, 0u}, cnt = 0, flag = heads ? 1u : 0u;
+    u32 v[NW], cnt = 0, flag = heads ? 1u : 0u;
+    cnt_zero<NW>(v);
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
-        if ((heads >> j) & 1u) { v[0] = v[1] = v[2] = v[3] = 0u; cnt = 0; }
-        cnt_add(v, (sy >> (4 * j)) & 15u); ++cnt;
+        if ((heads >> j) & 1u) { cnt_zero<NW>(v); cnt = 0; }
+        cnt_add<NW>(v, (sy >> (4 * j)) & 15u); ++cnt;
     }
     // segmented inclusive scan over the warp's threads
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const u32 a0 = __shfl_up_sync(FULL, v[0], o), a1 = __shfl_up_sync(FULL, v[1], o), a2 = __shfl_up_sync(FULL, v[2], o), a3 = __shfl_up_sync(FULL, v[3], o);
+        u32 av[NW];
+#pragma unroll
+        for (int q = 0; q < NW; ++q) av[q] = __shfl_up_sync(FULL, v[q], o);
         const u32 ac = __shfl_up_sync(FULL, cnt, o), af = __shfl_up_sync(FULL, flag, o);
         if (ln >= (u32)o) {
-            if (!flag) { v[0] += a0; v[1] += a1; v[2] += a2; v[3] += a3; cnt += ac; }
+            if (!flag) {
+#pragma unroll
+                for (int q = 0; q < NW; ++q) v[q] += av[q];
+                cnt += ac;
+            }
             flag |= af;
         }
     }
-    if (ln == 31) { S.wv[w][0] = v[0]; S.wv[w][1] = v[1]; S.wv[w][2] = v[2]; S.wv[w][3] = v[3]; S.wcnt[w] = cnt; S.wflag[w] = flag; }
+    if (ln == 31) {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) S.wv[w][q] = v[q];
+        S.wcnt[w] = cnt; S.wflag[w] = flag;
+    }
     // exclusive: what the threads before me accumulated since the last run head
-    u32 c[4], ccnt;
+    u32 c[NW], ccnt;
     {
-        c[0] = __shfl_up_sync(FULL, v[0], 1); c[1] = __shfl_up_sync(FULL, v[1], 1); c[2] = __shfl_up_sync(FULL, v[2], 1); c[3] = __shfl_up_sync(FULL, v[3], 1);
+#pragma unroll
+        for (int q = 0; q < NW; ++q) c[q] = __shfl_up_sync(FULL, v[q], 1);
         ccnt = __shfl_up_sync(FULL, cnt, 1);
         u32 cflag = __shfl_up_sync(FULL, flag, 1);
-        if (ln == 0) { c[0] = c[1] = c[2] = c[3] = 0u; ccnt = 0; cflag = 0; }
+        if (ln == 0) { cnt_zero<NW>(c); ccnt = 0; cflag = 0; }
         __syncthreads();
         if (!cflag) {                                // no run head in this warp before me: the run continues from earlier warps
             for (int ww = (int)w - 1; ww >= 0; --ww) {
-                c[0] += S.wv[ww][0]; c[1] += S.wv[ww][1]; c[2] += S.wv[ww][2]; c[3] += S.wv[ww][3]; ccnt += S.wcnt[ww];
+#pragma unroll
+                for (int q = 0; q < NW; ++q) c[q] += S.wv[ww][q];
+                ccnt += S.wcnt[ww];
                 if (S.wflag[ww]) break;
             }
         }
@@ -330,79 +358,88 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
     u32 badmask = 0, freshmask = 0;
     {
         u32 T0 = 0; bool fresh = false;
-        u32* const myscr = scratch + tid * 8;        // exclusive prefix sums of the current row, 16 x u16
+        u32* const myscr = scratch + tid * 8;        // exclusive prefix sums of the live counters of the current row, u16 each
         const u16* P = (const u16*)myscr;
-        v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; v[3] = c[3]; cnt = ccnt;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) v[q] = c[q];
+        cnt = ccnt;
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
             const u32 s = (sy >> (4 * j)) & 15u;
             const bool head = (heads >> j) & 1u;
-            if (head) { v[0] = v[1] = v[2] = v[3] = 0u; cnt = 0; }
+            if (head) { cnt_zero<NW>(v); cnt = 0; }
             if ((u32)j < nval) {
                 const u32 e = sorted[p0 + j];
                 if (j == 0 || head) {
-                    const uint4* rowp = (const uint4*)(tab + (u64)(e >> TT_SHIFT) * 32);
-                    uint4 r0 = rowp[0], r1 = rowp[1];
-                    fresh = (r0.x & 0xFFFFu) == 0;
-                    if (fresh) { r0 = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u); r1 = r0; }
-                    u32 o = 0; uint4 ex;
-                    ex.x = o * 0x10001u + (r0.x << 16); o += (r0.x & 0xFFFFu) + (r0.x >> 16);
-                    ex.y = o * 0x10001u + (r0.y << 16); o += (r0.y & 0xFFFFu) + (r0.y >> 16);
-                    ex.z = o * 0x10001u + (r0.z << 16); o += (r0.z & 0xFFFFu) + (r0.z >> 16);
-                    ex.w = o * 0x10001u + (r0.w << 16); o += (r0.w & 0xFFFFu) + (r0.w >> 16);
-                    ((uint4*)myscr)[0] = ex;
-                    ex.x = o * 0x10001u + (r1.x << 16); o += (r1.x & 0xFFFFu) + (r1.x >> 16);
-                    ex.y = o * 0x10001u + (r1.y << 16); o += (r1.y & 0xFFFFu) + (r1.y >> 16);
-                    ex.z = o * 0x10001u + (r1.z << 16); o += (r1.z & 0xFFFFu) + (r1.z >> 16);
-                    ex.w = o * 0x10001u + (r1.w << 16); o += (r1.w & 0xFFFFu) + (r1.w >> 16);
-                    ((uint4*)myscr)[1] = ex;
-                    T0 = o;
+                    const u8* rowp = tab + (u64)(e >> TT_SHIFT) * 32;
+                    u32 rw[2 * NW];                  // the live counters, two per word
+                    if (NW == 1) { const uint2 r = *(const uint2*)rowp; rw[0] = r.x; rw[1] = r.y; }
+                    else {
+#pragma unroll
+                        for (int q = 0; q < NW / 2; ++q) { const uint4 r = ((const uint4*)rowp)[q]; rw[4 * q] = r.x; rw[4 * q + 1] = r.y; rw[4 * q + 2] = r.z; rw[4 * q + 3] = r.w; }
+                    }
+                    fresh = (rw[0] & 0xFFFFu) == 0;
+                    u32 o = 0, ex[2 * NW];
+#pragma unroll
+                    for (int q = 0; q < 2 * NW; ++q) {
+                        const u32 r = fresh ? 0x00010001u : rw[q];
+                        ex[q] = o * 0x10001u + (r << 16); o += (r & 0xFFFFu) + (r >> 16);
+                    }
+                    if (NW == 1) *(uint2*)myscr = make_uint2(ex[0], ex[1]);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < NW / 2; ++q) ((uint4*)myscr)[q] = make_uint4(ex[4 * q], ex[4 * q + 1], ex[4 * q + 2], ex[4 * q + 3]);
+                    }
+                    T0 = o + DEAD;
                 }
                 const u32 pos = cnt;
                 const bool bad = pos >= 255u || T0 + 2 * pos >= limit;
                 freshmask |= (fresh ? 1u : 0u) << j;
                 if (!bad) {
-                    const u32 c0 = P[s], c1 = s < 15 ? (u32)P[s + 1] : T0;
+                    const u32 c0 = P[s], c1 = s < NS - 1 ? (u32)P[s + 1] : T0 - DEAD;
                     const u32 kk = s >> 2, sh = (s & 3u) * 8;
-                    const u32 vk = kk == 0 ? v[0] : kk == 1 ? v[1] : kk == 2 ? v[2] : v[3];
+                    u32 vk = v[0], nc = 0;
+#pragma unroll
+                    for (int q = 1; q < NW; ++q) { vk = kk == (u32)q ? v[q] : vk; nc += kk >= (u32)q ? bytesum(v[q - 1]) : 0u; }
                     const u32 nf = (vk >> sh) & 255u;
-                    u32 nc = bytesum(vk & ((1u << sh) - 1u));
-                    nc += kk > 0 ? bytesum(v[0]) : 0u; nc += kk > 1 ? bytesum(v[1]) : 0u; nc += kk > 2 ? bytesum(v[2]) : 0u;
+                    nc += bytesum(vk & ((1u << sh) - 1u));
                     S.x.trip[e & (TT - 1)] = TRIP(c1 - c0 + 2 * nf, c0 + 2 * nc, T0 + 2 * pos);
                 } else {
                     badmask |= 1u << j;
                     if (pos == 0 || !(pos - 1 >= 255u || T0 + 2 * (pos - 1) >= limit)) S.longs[atomicAdd(&S.n_long, 1u)] = (u16)(p0 + j - pos);
                 }
             }
-            cnt_add(v, s); ++cnt;
+            cnt_add<NW>(v, s); ++cnt;
         }
     }
     __syncthreads();
     // P3: the last member of every run the scan covered adds the run's counts to the row -- without reading it again: a row
     // that was fresh is stored whole (ones + counts), any other receives its non-zero words as fire-and-forget reductions
-    v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; v[3] = c[3];
+#pragma unroll
+    for (int q = 0; q < NW; ++q) v[q] = c[q];
     tails &= ~badmask & ((1u << nval) - 1u);
     if (tails) {
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
-            if ((heads >> j) & 1u) { v[0] = v[1] = v[2] = v[3] = 0u; }
-            cnt_add(v, (sy >> (4 * j)) & 15u);
+            if ((heads >> j) & 1u) cnt_zero<NW>(v);
+            cnt_add<NW>(v, (sy >> (4 * j)) & 15u);
             if ((tails >> j) & 1u) {
                 const u32 k = sorted[p0 + j] >> TT_SHIFT;
                 u32* rowp = (u32*)(tab + (u64)k * 32);
-                // byte counters -> 16-bit lanes, doubled
+                // byte counters -> 16-bit lanes, doubled; the dead counters keep their 1
                 u32 d[8];
-                d[0] = 2 * __byte_perm(v[0], 0u, 0x4140); d[1] = 2 * __byte_perm(v[0], 0u, 0x4342);
-                d[2] = 2 * __byte_perm(v[1], 0u, 0x4140); d[3] = 2 * __byte_perm(v[1], 0u, 0x4342);
-                d[4] = 2 * __byte_perm(v[2], 0u, 0x4140); d[5] = 2 * __byte_perm(v[2], 0u, 0x4342);
-                d[6] = 2 * __byte_perm(v[3], 0u, 0x4140); d[7] = 2 * __byte_perm(v[3], 0u, 0x4342);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    d[2 * q] = q < NW ? 2 * __byte_perm(v[q < NW ? q : 0], 0u, 0x4140) : 0u;
+                    d[2 * q + 1] = q < NW ? 2 * __byte_perm(v[q < NW ? q : 0], 0u, 0x4342) : 0u;
+                }
                 if ((freshmask >> j) & 1u) {
                     touched[atomicAdd(&S.n_touched, 1u)] = k;
                     ((uint4*)rowp)[0] = make_uint4(d[0] + 0x00010001u, d[1] + 0x00010001u, d[2] + 0x00010001u, d[3] + 0x00010001u);
                     ((uint4*)rowp)[1] = make_uint4(d[4] + 0x00010001u, d[5] + 0x00010001u, d[6] + 0x00010001u, d[7] + 0x00010001u);
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) if (d[q]) atomicAdd(&rowp[q], d[q]);
+                    for (int q = 0; q < 2 * NW; ++q) if (d[q]) atomicAdd(&rowp[q], d[q]);
                 }
             }
         }
@@ -412,7 +449,7 @@ __device__ void tab_scan_groups16(TabShared& S, const u32* sorted, u32* scratch,
 // F: FetchQ / FetchD (rc_model.cu). scratch: per-CTA global scratch for the touched-context list (M entries).
 template <int N, class F>
 __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8* tab, u32* touched, u64* trip,
-                           const Workspace& ws, long long& prof_t, int pb)
+                           const Workspace& ws, long long& prof_t, int pb, u32 live_words = 4)
 {
     const u32 tid = threadIdx.x, w = warp_id(), ln = lane_id(), lt = (1u << ln) - 1;
     const u32 passes = (key_bits + 9) / 10, pbits = (key_bits + passes - 1) / passes;
@@ -446,7 +483,9 @@ __device__ void tab_engine(TabShared& S, u32* scan, F f, u32 M, u32 key_bits, u8
         PROF_MARK(pb + 1);
         if (N == 16) {
             // ---- scan engine: counts by segmented prefix sums, rows met by every element in parallel
-            tab_scan_groups16(S, sorted, S.el[cur ^ 1], n, tab, touched);
+            if (live_words == 1) tab_scan_groups16<1>(S, sorted, S.el[cur ^ 1], n, tab, touched);
+            else if (live_words == 2) tab_scan_groups16<2>(S, sorted, S.el[cur ^ 1], n, tab, touched);
+            else tab_scan_groups16<4>(S, sorted, S.el[cur ^ 1], n, tab, touched);
             PROF_MARK(pb + 3);
             tab_long_groups<N>(S, sorted, n, tab, touched);
         } else {

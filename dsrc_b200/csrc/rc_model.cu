@@ -202,17 +202,29 @@ __device__ __forceinline__ void FetchQ::tile8(TabShared& S, u32 t0, u32 n)
     u64 pcw = 0; u32 jp = 0;
     if (fixed_len) jp = i % fixed_len; else pcw = *(const u64*)(pctx + i);
     u32 el[8];
+    // hash slots (TQualityModelBase::UpdateHash, QualityEncoder.h:77-89): slot t holds the symbol t+1 steps back for t < h, the mean
+    // of the symbols t+1 and t+2 steps back from slot h on. The two orders that exist for 16-symbol rows are written out with the
+    // slot shifts as multipliers (one multiply-add per slot and symbol); anything else takes the generic loop.
+    u32 a[12];                                        // a[i] = mean of r[i], r[i+1]
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = (r[i] + r[i + 1]) >> 1;
+    const u32 M1 = 1u << ebits, M2 = 1u << (2 * ebits), M3 = 1u << (3 * ebits), MP = 1u << pbits;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         u32 pc;
         if (fixed_len) { pc = plut[jp]; jp = jp + 1 == fixed_len ? 0u : jp + 1; } else pc = (u32)(pcw >> (8 * k)) & 255u;
-        u32 hash = 0;                                 // y[t] = r[5 + k - t]: symbol t steps back
+        u32 hash;
+        if (so == 4 && h == 2) hash = r[4 + k] + r[3 + k] * M1 + a[1 + k] * M2 + a[k] * M3;
+        else if (so == 3 && h == 1) hash = r[4 + k] + a[2 + k] * M1 + a[1 + k] * M2;
+        else {
+            hash = 0;                                 // y[t] = r[5 + k - t]: symbol t steps back
 #pragma unroll
-        for (int t = 0; t < 4; ++t) if ((u32)t < so) {
-            const u32 v = (u32)t < h ? r[4 + k - t] : ((r[4 + k - t] + r[3 + k - t]) >> 1);
-            hash |= v << (t * ebits);
+            for (int t = 0; t < 4; ++t) if ((u32)t < so) {
+                const u32 v = (u32)t < h ? r[4 + k - t] : a[3 + k - t];
+                hash |= v << (t * ebits);
+            }
         }
-        el[k] = ((((hash << pbits) | pc)) << TT_SHIFT) | (p + k);
+        el[k] = ((hash * MP + pc) << TT_SHIFT) | (p + k);
     }
     ((uint4*)S.el[0])[threadIdx.x * 2] = make_uint4(el[0], el[1], el[2], el[3]);
     ((uint4*)S.el[0])[threadIdx.x * 2 + 1] = make_uint4(el[4], el[5], el[6], el[7]);
@@ -532,7 +544,8 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
                 FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M; f.plut = TS.plut; f.fixed_len = fixed_len; f.jpos = 0;
                 f.ebits = 1; while ((1u << f.ebits) < st.q_count) ++f.ebits;
                 f.pbits = cfg.rescale > 8 ? 4 : 3;
-                tab_engine<16>(TS, S.scan, f, M, f.pbits + cfg.sym_order * f.ebits, tab, (u32*)bufA, trip, ws, prof_t, 16);
+                tab_engine<16>(TS, S.scan, f, M, f.pbits + cfg.sym_order * f.ebits, tab, (u32*)bufA, trip, ws, prof_t, 16,
+                               st.q_count <= 4 ? 1u : st.q_count <= 8 ? 2u : 4u);
             } else {
                 FetchD f; f.sq = ws.dcat + d.sym_base; f.ord = cfg.ord; f.bits = cfg.bits; f.prev = 0; f.M = M;
                 if (cfg.alpha == 4) tab_engine<4>(TS, S.scan, f, M, cfg.key_bits, tab, (u32*)bufA, trip, ws, prof_t, 24);
