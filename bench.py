@@ -114,7 +114,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (BASELINE configs[1]: 50 M)")
     ap.add_argument("--profile", type=int, default=0)
-    ap.add_argument("--inflight", type=int, default=4096, help="blocks per batch (one batch per stream slot)")
+    ap.add_argument("--inflight", type=int, default=8192, help="blocks per batch (one batch per stream slot); the range-coder chains of a batch take the same time for 1 or 16 K blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")

@@ -133,8 +133,8 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
     if (settings->dna_order || settings->quality_order) { if (rc_init_device() != cudaSuccess) { delete ctx; return DSRCGPU_E_CUDA; } }
     if (max_inflight_blocks == 0) {
-        u64 n = (512ull << 20) / max_block_bytes;          // ~0.5 GiB of FASTQ per batch
-        max_inflight_blocks = (u32)std::min<u64>(std::max<u64>(n, 1), 4096);
+        u64 n = (2048ull << 20) / max_block_bytes;         // ~2 GiB of FASTQ per batch: the range-coder chains of a batch are latency-bound,
+        max_inflight_blocks = (u32)std::min<u64>(std::max<u64>(n, 1), 8192);   // their launch takes the same time for 1 or 16 K blocks
     }
     ctx->max_inflight = max_inflight_blocks;
     // batches in flight (streams): 3 by default -- copies, parallel kernels and the range-coder chains of different batches overlap
