@@ -39,6 +39,15 @@ def small_cases():
     rq = synth.random_quals(1500)
     for d, q in [(6, 2), (9, 1)]:
         c.append(("randq60_d%d_q%d" % (d, q), rq, d, q, 0))
+    # the 16-symbol quality models by symbol count (the GPU scan engine is compiled per 4 / 8 / 16 live symbols): sticky and random
+    m12 = synth.illumina(900, seed=31, regime="mid12")
+    two = synth.illumina(900, seed=32, regime="two")
+    for d, q in [(6, 2), (3, 1)]:
+        c.append(("ill_mid12_d%d_q%d" % (d, q), m12, d, q, 0))
+        c.append(("ill_two_d%d_q%d" % (d, q), two, d, q, 0))
+    c.append(("randq12_d6_q2", synth.random_quals(900, seed=33, n_levels=12), 6, 2, 0))
+    c.append(("randq7_d6_q2", synth.random_quals(900, seed=34, n_levels=7), 6, 2, 0))
+    c.append(("randq3_d9_q1", synth.random_quals(900, seed=35, n_levels=3), 9, 1, 0))
     # inputs found by tools/fuzz_parity.py: a two-symbol Huffman tree whose zero-frequency symbol is the larger one (the reference
     # forces both frequencies to 1 in place, src/huffman.cpp:128-133, so the former minimum stays the left child), and very short
     # variable-length reads with '+' title repetition

@@ -30,6 +30,10 @@ def illumina(n_reads, length=150, seed=1234, regime="binned", n_rate=2e-3, tail_
     rng = np.random.default_rng(seed)
     if regime == "binned":
         levels = np.array([2, 12, 23, 37], dtype=np.uint8)
+    elif regime == "mid12":          # 12 sticky levels (+ the transferred N): 9..16 symbols, still the 16-symbol models
+        levels = np.array([2, 6, 9, 12, 15, 18, 21, 24, 27, 30, 34, 38], dtype=np.uint8)
+    elif regime == "two":            # <= 4 symbols
+        levels = np.array([11, 37], dtype=np.uint8)
     else:
         levels = np.arange(0, 41, dtype=np.uint8)
     q = _markov_quals(rng, n_reads, length, levels)
