@@ -173,6 +173,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's own log lines (e.g. its version banner) off stdout: one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ds = _lib.Dataset(33, 0, 0)
