@@ -148,3 +148,51 @@ class Ref:
 
     def decompress_file(self, src, dst, threads=1):
         return self.lib.ref_decompress_file(src.encode(), dst.encode(), threads)
+
+
+def shim_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdsrcshim.so"))
+
+
+class Shim:
+    """host/BlockCompressorGpu.h -- the C++ binding of INTEGRATION.md, compiled against the reference's own headers
+    (oracle/shim_harness.cpp) -- driven exactly like Ref: one instance == one worker's compressor, on the GPU."""
+
+    def __init__(self, qoff=33, plus_rep=0, dna_order=0, qua_order=0, crc=False, max_block=1 << 20):
+        self.lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libdsrcshim.so"))
+        L = self.lib
+        L.shim_bc_create.restype = C.c_void_p
+        L.shim_bc_create.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32]
+        L.shim_bc_destroy.argtypes = [C.c_void_p]
+        L.shim_bc_store.restype = C.c_longlong
+        L.shim_bc_store.argtypes = [C.c_void_p, C.c_char_p, C.c_ulonglong, _u8p, C.c_ulonglong, _u64p, _u64p]
+        L.shim_bc_read.restype = C.c_longlong
+        L.shim_bc_read.argtypes = [C.c_void_p, C.c_char_p, C.c_ulonglong, _u8p, C.c_ulonglong]
+        self.h = L.shim_bc_create(qoff, plus_rep, 0, dna_order, qua_order, 0, int(crc), max_block)
+        if not self.h:
+            raise RuntimeError("BlockCompressorGpu: no CUDA device")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.shim_bc_destroy(self.h)
+        except Exception:
+            pass
+
+    def store(self, chunk):
+        cap = len(chunk) * 2 + (1 << 16)
+        out = (C.c_uint8 * cap)()
+        raw = (C.c_uint64 * 4)()
+        cmp_ = (C.c_uint64 * 4)()
+        n = self.lib.shim_bc_store(self.h, chunk, len(chunk), out, cap, raw, cmp_)
+        if n < 0:
+            raise RuntimeError("shim store failed: %d" % n)
+        return bytes(out[:n]), list(raw), list(cmp_)
+
+    def read(self, blk, cap=None):
+        cap = cap or (len(blk) * 40 + (1 << 20))
+        out = (C.c_uint8 * cap)()
+        n = self.lib.shim_bc_read(self.h, blk, len(blk), out, cap)
+        if n < 0:
+            raise RuntimeError("shim read failed: %d" % n)
+        return bytes(out[:n])
