@@ -3,6 +3,7 @@
 // ref_harness.cpp exposes comp::BlockCompressor, so tests/test_gpu_shim.py can drive both through identical calls and compare
 // bytes. Built into oracle/_ref/libdsrcshim.so (links ../../dsrc_b200/libdsrc_b200.so; git-ignored, travels to the GPU box).
 #include "../host/BlockCompressorGpu.h"
+#include "../host/DsrcOperatorGpu.h"
 #include "Buffer.h"
 #include <cstring>
 
@@ -84,6 +85,34 @@ long long shim_bc_read(void* h_, const unsigned char* in_, unsigned long long si
 		return -1;
 	std::memcpy(out_, chunk.data.Pointer(), chunk.size);
 	return (long long)chunk.size;
+}
+
+// whole-file operators, same signatures as ref_compress_file_crc / ref_decompress_file of ref_harness.cpp
+int shim_compress_file(const char* in_, const char* out_, int dnaLevel, int quaLevel, int bufMB, unsigned qoff, int crc, char* err, int errCap)
+{
+	comp::InputParameters p;
+	p.inputFilename = in_;
+	p.outputFilename = out_;
+	p.dnaCompressionLevel = dnaLevel;
+	p.qualityCompressionLevel = quaLevel;
+	p.fastqBufferSizeMB = bufMB;
+	p.qualityOffset = qoff;
+	p.calculateCrc32 = crc != 0;
+	comp::DsrcCompressorGpu op;
+	bool ok = op.Process(p);
+	if (err && errCap > 0) { std::strncpy(err, op.GetError().c_str(), errCap - 1); err[errCap - 1] = 0; }
+	return ok ? 0 : -1;
+}
+
+int shim_decompress_file(const char* in_, const char* out_, char* err, int errCap)
+{
+	comp::InputParameters p;
+	p.inputFilename = in_;
+	p.outputFilename = out_;
+	comp::DsrcDecompressorGpu op;
+	bool ok = op.Process(p);
+	if (err && errCap > 0) { std::strncpy(err, op.GetError().c_str(), errCap - 1); err[errCap - 1] = 0; }
+	return ok ? 0 : -1;
 }
 
 } // extern "C"

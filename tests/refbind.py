@@ -196,3 +196,18 @@ class Shim:
         if n < 0:
             raise RuntimeError("shim read failed: %d" % n)
         return bytes(out[:n])
+
+    # host/DsrcOperatorGpu.h: IDsrcOperator::Process over the batch ABI (file to file)
+    def compress_file(self, src, dst, d, q, buf_mb, qoff=0, crc=False):
+        L = self.lib
+        L.shim_compress_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_char_p, C.c_int]
+        err = C.create_string_buffer(512)
+        rc = L.shim_compress_file(src.encode(), dst.encode(), d, q, buf_mb, qoff, int(crc), err, 512)
+        return rc, err.value.decode()
+
+    def decompress_file(self, src, dst):
+        L = self.lib
+        L.shim_decompress_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        err = C.create_string_buffer(512)
+        rc = L.shim_decompress_file(src.encode(), dst.encode(), err, 512)
+        return rc, err.value.decode()

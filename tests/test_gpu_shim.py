@@ -39,3 +39,40 @@ def test_shim_crc_blocks():
     got, _, _ = gpu.store(chunk)
     assert got == exp
     assert gpu.read(exp) == data
+
+
+@pytest.mark.parametrize("d,q,buf_mb,crc", [(2, 2, 1, False), (0, 0, 1, False), (3, 1, 1, True)])
+def test_operator_archive_is_byte_identical_to_dsrc_c_t1(tmp_path, d, q, buf_mb, crc):
+    """host/DsrcOperatorGpu.h: DsrcCompressorGpu / DsrcDecompressorGpu (IDsrcOperator::Process, file to file) against the
+    reference's single-thread operators (`dsrc c -t1` / `dsrc d`), in both directions."""
+    import synth
+    big = synth.illumina(8000, seed=7)
+    src = str(tmp_path / "in.fastq")
+    open(src, "wb").write(big)
+    ref = refbind.Ref()
+    gpu = refbind.Shim()
+    a_ref, a_gpu = str(tmp_path / "ref.dsrc"), str(tmp_path / "gpu.dsrc")
+    assert ref.compress_file(src, a_ref, d, q, buf_mb, threads=1, crc=crc) == 0
+    rc, err = gpu.compress_file(src, a_gpu, d, q, buf_mb, crc=crc)
+    assert rc == 0, err
+    assert open(a_gpu, "rb").read() == open(a_ref, "rb").read()
+    back_gpu, back_ref = str(tmp_path / "gpu.fastq"), str(tmp_path / "ref.fastq")
+    rc, err = gpu.decompress_file(a_ref, back_gpu)          # the GPU operator reads the reference's archive
+    assert rc == 0, err
+    assert open(back_gpu, "rb").read() == big
+    assert ref.decompress_file(a_gpu, back_ref, threads=1) == 0   # and the reference reads the GPU operator's
+    assert open(back_ref, "rb").read() == big
+
+
+def test_operator_errors_follow_the_reference(tmp_path):
+    gpu = refbind.Shim()
+    rc, err = gpu.compress_file(str(tmp_path / "missing.fastq"), str(tmp_path / "x.dsrc"), 2, 2, 1)
+    assert rc != 0 and "Cannot open file to read:" in err
+    bad = str(tmp_path / "bad.fastq")
+    open(bad, "wb").write(b"this is not FASTQ\n" * 10)
+    rc, err = gpu.compress_file(bad, str(tmp_path / "y.dsrc"), 2, 2, 1)
+    assert rc != 0 and err
+    junk = str(tmp_path / "junk.dsrc")
+    open(junk, "wb").write(b"\x00" * 100)
+    rc, err = gpu.decompress_file(junk, str(tmp_path / "z.fastq"))
+    assert rc != 0 and "Invalid archive" in err
