@@ -4,6 +4,7 @@
 // bytes. Built into oracle/_ref/libdsrcshim.so (links ../../dsrc_b200/libdsrc_b200.so; git-ignored, travels to the GPU box).
 #include "../host/BlockCompressorGpu.h"
 #include "../host/DsrcOperatorGpu.h"
+#include "../host/DsrcModuleGpu.h"
 #include "Buffer.h"
 #include <cstring>
 
@@ -113,6 +114,28 @@ int shim_decompress_file(const char* in_, const char* out_, char* err, int errCa
 	bool ok = op.Process(p);
 	if (err && errCap > 0) { std::strncpy(err, op.GetError().c_str(), errCap - 1); err[errCap - 1] = 0; }
 	return ok ? 0 : -1;
+}
+
+// wrap::DsrcModule surface: Configurable setters, then Compress / Decompress; returns 0 or -1 with the exception text
+int shim_module_roundtrip(const char* fastq_, const char* archive_, const char* back_, int dnaLevel, int quaLevel, int bufMB, int crc,
+						  char* err, int errCap)
+{
+	try
+	{
+		wrap::DsrcModuleGpu m;
+		m.SetDnaCompressionLevel(dnaLevel);
+		m.SetQualityCompressionLevel(quaLevel);
+		m.SetFastqBufferSizeMB(bufMB);
+		m.SetCrc32Checking(crc != 0);
+		m.Compress(fastq_, archive_);
+		m.Decompress(archive_, back_);
+		return 0;
+	}
+	catch (const DsrcException& e)
+	{
+		if (err && errCap > 0) { std::strncpy(err, e.what(), errCap - 1); err[errCap - 1] = 0; }
+		return -1;
+	}
 }
 
 } // extern "C"

@@ -211,3 +211,11 @@ class Shim:
         err = C.create_string_buffer(512)
         rc = L.shim_decompress_file(src.encode(), dst.encode(), err, 512)
         return rc, err.value.decode()
+
+    # host/DsrcModuleGpu.h: wrap::DsrcModule surface (Configurable setters + Compress/Decompress)
+    def module_roundtrip(self, fastq, archive, back, d, q, buf_mb, crc=False):
+        L = self.lib
+        L.shim_module_roundtrip.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        err = C.create_string_buffer(512)
+        rc = L.shim_module_roundtrip(fastq.encode(), archive.encode(), back.encode(), d, q, buf_mb, int(crc), err, 512)
+        return rc, err.value.decode()

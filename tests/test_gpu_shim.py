@@ -76,3 +76,19 @@ def test_operator_errors_follow_the_reference(tmp_path):
     open(junk, "wb").write(b"\x00" * 100)
     rc, err = gpu.decompress_file(junk, str(tmp_path / "z.fastq"))
     assert rc != 0 and "Invalid archive" in err
+
+
+def test_module_compress_decompress(tmp_path):
+    """host/DsrcModuleGpu.h: wrap::DsrcModule's surface (Configurable setters, Compress, Decompress, DsrcException on error)."""
+    import synth
+    big = synth.illumina(6000, seed=9, regime="full")
+    src, arc, back, a_ref = (str(tmp_path / n) for n in ("in.fastq", "m.dsrc", "m.fastq", "ref.dsrc"))
+    open(src, "wb").write(big)
+    gpu = refbind.Shim()
+    rc, err = gpu.module_roundtrip(src, arc, back, 2, 2, 1)
+    assert rc == 0, err
+    assert open(back, "rb").read() == big
+    assert refbind.Ref().compress_file(src, a_ref, 2, 2, 1, threads=1) == 0
+    assert open(arc, "rb").read() == open(a_ref, "rb").read()
+    rc, err = gpu.module_roundtrip(str(tmp_path / "missing"), arc, back, 2, 2, 1)
+    assert rc != 0 and "Cannot open file to read:" in err
