@@ -161,3 +161,31 @@ def test_c_abi_format_helpers_match_oracle():
         assert bytes(foot) == arc[40 + total:]
         assert int(off[0]) == 40 and int(off[nb - 1]) + int(ln[nb - 1]) == 40 + total
     assert L.dsrcgpu_read_archive_index(b"\0" * 64, 64, C.byref(n), None, None, 0, None, None) != 0
+
+
+def test_cpp_operator_host_paths_need_no_device(tmp_path):
+    """host/DsrcOperatorGpu.h through the shim harness: the failures the reference reports before any block is coded (missing input,
+    not FASTQ, not an archive) come back through IDsrcOperator::GetError with the reference's texts -- no device involved."""
+    import ctypes as C
+    import os
+    import refbind
+    if not refbind.shim_available():
+        import pytest
+        pytest.skip("oracle/_ref/libdsrcshim.so not built")
+    L = C.CDLL(os.path.join(refbind.ROOT, "oracle", "_ref", "libdsrcshim.so"))
+    for sym in ("shim_bc_create", "shim_bc_store", "shim_bc_read", "shim_compress_file", "shim_decompress_file", "shim_module_roundtrip"):
+        assert hasattr(L, sym)
+    L.shim_compress_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_char_p, C.c_int]
+    L.shim_decompress_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    err = C.create_string_buffer(512)
+    out = str(tmp_path / "o").encode()
+    assert L.shim_compress_file(str(tmp_path / "missing").encode(), out, 2, 2, 1, 0, 0, err, 512) != 0
+    assert b"Cannot open file to read:" in err.value
+    bad = tmp_path / "bad.fastq"
+    bad.write_bytes(b"this is not FASTQ\n" * 10)
+    assert L.shim_compress_file(str(bad).encode(), out, 2, 2, 1, 0, 0, err, 512) != 0
+    assert b"Error analyzing FASTQ dataset" in err.value
+    junk = tmp_path / "junk.dsrc"
+    junk.write_bytes(b"\0" * 100)
+    assert L.shim_decompress_file(str(junk).encode(), out, err, 512) != 0
+    assert b"Invalid archive" in err.value
