@@ -5,17 +5,18 @@
 // 281-342), TSymbolCoderRC (src/SymbolCoderRC.h:24-93), RangeEncoder (src/RangeCoder.h:51-84).
 //
 // The reference codes symbol after symbol: look the context row up in a 32 KB .. 64 MB table, sum it, emit,
-// bump one counter. On a GPU that is one DRAM round trip per symbol. Two observations remove the table:
+// bump one counter. On a GPU that is one DRAM round trip per symbol. Two observations split the work:
 //   (1) the context of symbol i is a pure function of the INPUT (the previous <= 5 symbols and the read
 //       position), never of the coder state -- so all contexts of a block are computable in parallel;
 //   (2) the adaptive row a symbol sees is determined by the earlier symbols of the SAME context only:
 //       freq = 1 + 2*#(same ctx, same sym before), cum/tot likewise, with the halving rescale of
 //       TSymbolCoderRC::Rescale applied when tot crosses 2^16 - 2N.
-// So per block (one CTA): build (ctx, sym, index) keys -> stable LSD radix sort by ctx in HBM scratch ->
-// every context becomes a contiguous run in original order -> threads walk runs with N 16-bit counters in
-// shared memory and write the exact (freq, cum, tot) triple each symbol would have met.  What remains serial
-// is only RangeEncoder::EncodeFrequency over the triples: k_rc_encode runs one thread per (block, stream),
-// thousands of independent chains in flight, each a dozen integer instructions per symbol.
+// So the MODEL (the exact (freq, cum, tot) triple each symbol would meet) is computed block-parallel by k_model, one CTA per
+// block, with one of three engines -- the shared-memory direct engine for 4-symbol DNA (model_dna.cuh), the tile/table engine
+// with the scan engine for rows of <= 16 symbols (model_tab.cuh), the sort engine in this file for larger alphabets
+// (stable LSD radix sort by context in HBM scratch, then every context is a contiguous run in original order) -- and what
+// remains serial is only RangeEncoder::EncodeFrequency over the triples: k_rc_encode, one thread per (block, stream).
+// DESIGN.md section 4 has the full account.
 #include "common.cuh"
 #include "kernels.h"
 #include <cstddef>
