@@ -59,7 +59,8 @@ enum { DSRCGPU_STREAM_META = 0, DSRCGPU_STREAM_TAG = 1, DSRCGPU_STREAM_DNA = 2, 
 
 /* == BlockCompressor::BlockCompressor(datasetType, settings)  (src/BlockCompressor.cpp:53-94).
  * max_block_bytes: largest FASTQ block that will be submitted (CLI: -b MB << 20);
- * max_inflight_blocks: blocks processed per internal batch (0 = choose from free HBM). */
+ * max_inflight_blocks: blocks processed per internal batch (0 = about 2 GiB of FASTQ, at most 8192 blocks; the workspace of a batch is
+ * about 13x its FASTQ bytes, and 3 batches are in flight). */
 int dsrcgpu_create(dsrcgpu_ctx** ctx, int device, const dsrcgpu_dataset_t* dataset,
                    const dsrcgpu_settings_t* settings, uint32_t max_block_bytes, uint32_t max_inflight_blocks);
 void dsrcgpu_destroy(dsrcgpu_ctx* ctx);
