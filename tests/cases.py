@@ -48,6 +48,12 @@ def small_cases():
     c.append(("randq12_d6_q2", synth.random_quals(900, seed=33, n_levels=12), 6, 2, 0))
     c.append(("randq7_d6_q2", synth.random_quals(900, seed=34, n_levels=7), 6, 2, 0))
     c.append(("randq3_d9_q1", synth.random_quals(900, seed=35, n_levels=3), 9, 1, 0))
+    # the same models with a different read length per record (position bucket per record instead of the fixed-length table)
+    vl4 = synth.varlen_binned(700, seed=41)
+    vl12 = synth.varlen_binned(700, seed=42, levels=(2, 6, 9, 12, 15, 18, 21, 24, 27, 30, 34, 38))
+    c.append(("varlen_binned_d6_q2", vl4, 6, 2, 0))
+    c.append(("varlen_binned_d3_q1", vl4, 3, 1, 0))
+    c.append(("varlen_mid12_d6_q2", vl12, 6, 2, 0))
     # inputs found by tools/fuzz_parity.py: a two-symbol Huffman tree whose zero-frequency symbol is the larger one (the reference
     # forces both frequencies to 1 in place, src/huffman.cpp:128-133, so the former minimum stays the left child), and very short
     # variable-length reads with '+' title repetition

@@ -122,6 +122,20 @@ def skewed(n_reads, length=150, seed=8, p_major=0.97):
     return b"".join(b"@SK.%d 1:N:0\n" % (i + 1) + seq[i].tobytes() + b"\n+\n" + qual[i].tobytes() + b"\n" for i in range(n_reads))
 
 
+def varlen_binned(n_reads, seed=21, levels=(2, 12, 23, 37), lo=30, hi=170):
+    """variable-length reads with few sticky quality levels: the 16-symbol quality models with per-record position buckets
+    (TTranslationalQualityEncoder::Encode, j * rescale / len with a different len per read) over many tiles."""
+    rng = np.random.default_rng(seed)
+    lv = np.array(levels, dtype=np.uint8)
+    lines = []
+    for i in range(n_reads):
+        L = int(rng.integers(lo, hi + 1))
+        s = BASES[rng.integers(0, 4, size=L)]
+        q = _markov_quals(rng, 1, L, lv)[0]
+        lines.append(b"@VL.%d len=%d\n" % (i + 1, L) + s.tobytes() + b"\n+\n" + (q + 33).astype(np.uint8).tobytes() + b"\n")
+    return b"".join(lines)
+
+
 def random_quals(n_reads, length=150, seed=9, n_levels=60):
     """uniformly random qualities over many levels: tens of thousands of distinct order-2 contexts in one block
     (exercises the 64-symbol models and, on the GPU decode path, the full-table retry of a filled context hash)."""
