@@ -694,11 +694,13 @@ static void cut_skip_eol(const u8* d, u64& p, u64 size, bool& crlf)
 extern "C" uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks)
 {
     u64 start = 0, nb = 0; bool crlf = false;
+    bool tail_only = false;     // the previous full window ended exactly at EOF: the next Read() returns 0 and the chunk is the
+                                // carry-over as it stands -- no "- 1" for the final newline, no CRLF adjustment (FastqStream.cpp:41-69)
     if (cbuf <= 8192) return 0;
     while (start < size) {
         const u64 avail = size - start;
         u64 blk, adv;
-        if (avail >= cbuf) {
+        if (!tail_only && avail >= cbuf) {
             // the window is full: resume 8 KiB before its end, cut at the next line that starts a record
             const u8* w = data + start; u64 p = cbuf - 8192;
             cut_skip_eol(w, p, cbuf, crlf); ++p;
@@ -707,7 +709,11 @@ extern "C" uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint6
             cut_skip_eol(w, p, cbuf, crlf); ++p;
             if (p < cbuf && w[p] == '@') cand = p;      // the first '@' line was a quality string
             adv = cand; blk = cand - 1 - (crlf ? 1 : 0);
-        } else { adv = avail; blk = avail - 1 - (crlf ? 1 : 0); }
+            tail_only = avail == cbuf;
+        } else {
+            const u64 drop = tail_only ? 0 : 1 + (crlf ? 1 : 0);
+            adv = avail; blk = avail > drop ? avail - drop : 0;
+        }
         if (nb < max_blocks && off && len) { off[nb] = start; len[nb] = (u32)blk; }
         ++nb; start += adv;
     }

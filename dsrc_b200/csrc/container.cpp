@@ -89,13 +89,16 @@ extern "C" int dsrcgpu_read_archive_index(const uint8_t* arc, uint64_t size, uin
     if (!arc || !n_blocks) return DSRCGPU_E_ARG;
     if (size < 40 || arc[0] != 0xAA || arc[1] != 2) return DSRCGPU_E_MALFORMED;
     const u32 fsize = rd32(arc + 4); const u64 foff = rd64(arc + 8), n = rd64(arc + 24);
-    if (n == 0 || foff > size || fsize > size - foff || fsize < 1 + 4 * n + 13 || arc[foff] != 0xCC) return DSRCGPU_E_MALFORMED;
+    // the header is untrusted: bound the block count by what the footer and the block area can hold BEFORE it enters any arithmetic
+    // (4 * n wraps in 64 bits), every block is at least the 16-byte meta header
+    if (foff < 40 || foff > size || fsize > size - foff || fsize < 14) return DSRCGPU_E_MALFORMED;
+    if (n == 0 || n > ((u64)fsize - 14) / 4 || n > (foff - 40) / 16 + 1 || arc[foff] != 0xCC) return DSRCGPU_E_MALFORMED;
     *n_blocks = n;
     const u8* f = arc + foff;
     u64 p = 40;
     for (u64 i = 0; i < n; ++i) {
         const u32 v = (u32)f[1 + 4 * i] | ((u32)f[2 + 4 * i] << 8) | ((u32)f[3 + 4 * i] << 16) | ((u32)f[4 + 4 * i] << 24);
-        if (p + v > foff) return DSRCGPU_E_MALFORMED;
+        if (v > foff - p) return DSRCGPU_E_MALFORMED;
         if (i < max_blocks) { if (blk_off) blk_off[i] = p; if (blk_len) blk_len[i] = v; }
         p += v;
     }

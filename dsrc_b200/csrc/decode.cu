@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_tags(Workspace ws, uint2* pool_
             DField& f = fl[i];
             f.hg = 0xFFFFFFFFu; f.hl = 0xFFFFFFFFu; f.rle_len = 0; f.rle_sym = 0; f.prev = 0; f.var_stat = 0; f.is_numeric = 0; f.is_len_constant = 0;
             f.sep = (u8)r.byte(); f.is_constant = r.byte() != 0;
-            if (f.is_constant) { f.len = r.be32(); if (f.len >= 4096) { status = ST_MALFORMED; break; } f.data_pos = r.pos; r.pos += f.len; continue; }
+            if (f.is_constant) { f.len = r.be32(); if (f.len >= 4096 || (u64)r.pos + f.len > d.in_len) { status = ST_MALFORMED; break; } f.data_pos = r.pos; r.pos += f.len; continue; }
             f.is_numeric = r.byte() != 0;
             if (f.is_numeric) {
                 f.scheme = (u8)r.byte(); f.min_value = (i32)r.be32();
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_tags(Workspace ws, uint2* pool_
             f.len = r.be32(); f.max_len = r.be32(); f.min_len = r.be32();
             if (f.len >= 4096 || f.max_len >= 4096 || f.min_len > f.max_len) { status = ST_MALFORMED; break; }
             f.bits_len = dsrc_bit_length((u64)(f.max_len - f.min_len));
+            if ((u64)r.pos + f.len + (f.len + 7) / 8 > d.in_len) { status = ST_MALFORMED; break; }   // a corrupt length must not send the copies below past the block
             f.data_pos = r.pos; r.pos += f.len;
             f.ham_pos = r.pos; r.pos += (f.len + 7) / 8;     // len mask bits, MSB first, then a flush
             r.flush();

@@ -480,11 +480,13 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
     for (u32 blk = next_block(); blk < ws.n_blocks; blk = next_block()) {
         const BlockDesc& d = ws.desc[blk];
         BlockState& st = ws.state[blk];
-        if (st.status != ST_OK) continue;
-        // ---- scheme selection
+        // ---- scheme selection. Only thread 0 looks at (and may set) the block's status; everybody else learns the outcome from
+        // shared memory after the barrier, so the whole CTA takes the same path through next_block()'s barriers
         if (tid == 0) {
-            S.ok = 1;
-            if (QUALITY) {
+            S.ok = st.status == ST_OK;
+            S.M = 0;
+            if (!S.ok) {}
+            else if (QUALITY) {
                 u32 sc = quality_order_scheme(st, ws.qua_order);
                 st.q_scheme = (u8)sc;
                 if (sc == 255) S.ok = 0;                        // SchemeNone: just the scheme byte
@@ -500,7 +502,7 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
                 }
                 S.M = st.d_total;
             }
-            if (S.M > arena_stride) { S.ok = 0; st.status = ST_OVERFLOW; }
+            if (S.ok && S.M > arena_stride) { S.ok = 0; st.status = ST_OVERFLOW; }
         }
         if (QUALITY) S.rank[tid] = st.qrank[tid];
         __syncthreads();

@@ -1360,21 +1360,23 @@ static u64 next_record_pos(const u8* d, u64 pos, u64 size, int* crlf) /* FastqSt
 u64 dsrc_oracle_cut_blocks(const u8* file, u64 size, u64 cbuf, u64* off, u64* len, u64 max_blocks)
 {
     /* ReadNextChunk (FastqStream.cpp:18-72): buffer = carry-over + fresh bytes == file[p, p+cbuf) */
-    u64 p = 0, nb = 0; int crlf = 0, eof = 0;
+    u64 p = 0, nb = 0; int crlf = 0, eof = 0, tail_only = 0;
     while (!eof) {
         u64 avail = size - p, blk_len;
         /* Read() returned r bytes; the carry-over (p..) is part of the cbuf window */
-        if (avail >= cbuf && cbuf > 8192) {          /* r == toRead: somewhere before the end */
+        if (!tail_only && avail >= cbuf && cbuf > 8192) {   /* r == toRead: somewhere before the end */
             u64 end = next_record_pos(file + p, cbuf - 8192, cbuf, &crlf);
             blk_len = end - 1 - (crlf ? 1 : 0);
             if (nb < max_blocks) { off[nb] = p; len[nb] = blk_len; }
             nb++; p += end;
-            if (p == size) {                          /* next Read returns 0 -> eof, chunk = carry-over only */
-                eof = 1;
-            }
-        } else {                                      /* at the end of file: r < toRead */
+            /* the window ended exactly at EOF: the next Read returns 0 (the `else` of :66-69), the chunk is the
+               carry-over as it stands -- size = bufferSize, no "- 1", no CRLF adjustment */
+            if (avail == cbuf) tail_only = 1;
+            if (p == size) eof = 1;
+        } else {                                      /* at the end of file: r < toRead (:57-64), or r == 0 after an exact window */
+            u64 drop = tail_only ? 0 : 1 + (crlf ? 1u : 0u);
             if (avail == 0) break;
-            blk_len = avail - 1 - (crlf ? 1 : 0);
+            blk_len = avail > drop ? avail - drop : 0;
             if (nb < max_blocks) { off[nb] = p; len[nb] = blk_len; }
             nb++; eof = 1;
         }

@@ -27,7 +27,7 @@ def sha(b):
 def main():
     out = {"generator": "tests/golden/make_golden.py", "reference": "refresh-bio/DSRC 2.02 @ /root/reference, g++ -O2 -DNDEBUG -std=c++11",
            "cases": {}, "archives": {}}
-    for name, data, d, q, pr in cases.small_cases():
+    for name, data, d, q, pr in cases.all_cases():
         r = refbind.Ref(33, pr, d, q)
         cold, raw, cmp_ = r.store(data[:-1])
         warm, _, _ = r.store(data[:-1])

@@ -156,3 +156,65 @@ def changing_titles(seed=12):
         q = (rng.integers(20, 41, size=100) + 33).astype(np.uint8)
         a.append(b"@r%d/%d x=%d\n" % (i + 1, 1 + i % 2, int(rng.integers(0, 19))) + s.tobytes() + b"\n+\n" + q.tobytes() + b"\n")
     return b"".join(a) + illumina(3200, seed=seed + 1, small_field=True) + ion454(1500, seed=seed + 2)
+
+
+def exact_size(size, seed=3, crlf=False, base_reads=10000):
+    """a FASTQ file of exactly `size` bytes (the last title is padded): hits the reader's EOF-on-refill branch when `size` makes a
+    full chunk window end exactly at the end of the file (src/FastqStream.cpp:41-69: Read() returns 0, the chunk is the bare carry-over)"""
+    big = illumina(base_reads, seed=seed, crlf=crlf)
+    eol = b"\r\n" if crlf else b"\n"
+    recs = big.split(eol)
+    out, tot, i = [], 0, 0
+    while True:
+        rec = eol.join(recs[i:i + 4]) + eol
+        assert i + 4 < len(recs), "base too small"
+        if tot + len(rec) + 400 > size:
+            break
+        out.append(rec)
+        tot += len(rec)
+        i += 4
+    ln = 50
+    tl = size - tot - (len(eol) * 4 + ln * 2 + 1)
+    out.append(b"@" + b"x" * (tl - 1) + eol + b"A" * ln + eol + b"+" + eol + b"I" * ln + eol)
+    out = b"".join(out)
+    assert len(out) == size
+    return out
+
+
+IUPAC_ALL = b"NRWSKMDVHBYXU.-"      # indices 4..18 of the reference's symbol table (src/RecordsProcessor.cpp:180-207)
+
+
+def block_scale(n_reads=1000, length=150, n_levels=41, sticky=False, seed=1, low_amb=0.0, low_codes=b"N", high_amb=0.0,
+                high_codes=b"N", tail_frac=0.0, tail_max=60, varlen=False, q_lo=0):
+    """Vectorised block-scale generator (>= 256 KiB for 1000 x 150 bp) for the model shapes the small catalogue does not reach:
+    n_levels quality values (iid, or a sticky chain), ambiguity codes with q < 7 (`low_*`: transferred into the quality byte, any
+    IUPAC code -- SURVEY a4) and with q >= 7 (`high_*`: they stay in the DNA stream, so only N/R/W/S -- SURVEY 8-Q9), '#' tails,
+    optional per-read lengths. Quality values start at q_lo (>= 7 keeps `low` codes the only symbols below 7)."""
+    rng = np.random.default_rng(seed)
+    lv = (q_lo + np.arange(n_levels)).astype(np.uint8)
+    if sticky:
+        q = _markov_quals(rng, n_reads, length, lv, stay=0.9)
+    else:
+        q = lv[rng.integers(0, n_levels, size=(n_reads, length))]
+    seq = BASES[rng.integers(0, 4, size=(n_reads, length))].copy()
+    lens = rng.integers(max(20, length // 3), length + 1, size=n_reads) if varlen else np.full(n_reads, length)
+    if tail_frac:
+        t = np.where(rng.random(n_reads) < tail_frac, rng.integers(1, tail_max + 1, size=n_reads), 0)
+        q = np.where(np.arange(length)[None, :] >= (lens - np.minimum(t, lens - 1))[:, None], 2, q).astype(np.uint8)
+    if high_amb:
+        m = rng.random((n_reads, length)) < high_amb
+        codes = np.frombuffer(high_codes, dtype=np.uint8)[rng.integers(0, len(high_codes), size=(n_reads, length))]
+        seq = np.where(m, codes, seq)
+        q = np.where(m, np.maximum(q, 7), q).astype(np.uint8)
+    if low_amb:
+        m = rng.random((n_reads, length)) < low_amb
+        codes = np.frombuffer(low_codes, dtype=np.uint8)[rng.integers(0, len(low_codes), size=(n_reads, length))]
+        seq = np.where(m, codes, seq)
+        q = np.where(m, rng.integers(0, 7, size=(n_reads, length)), q).astype(np.uint8)
+    qual = (q + 33).astype(np.uint8)
+    x = rng.integers(1000, 30000, size=n_reads)
+    out = []
+    for i in range(n_reads):
+        ln = int(lens[i])
+        out.append(b"@B.%d %d:%d\n" % (i + 1, x[i], 7 * i) + seq[i, :ln].tobytes() + b"\n+\n" + qual[i, :ln].tobytes() + b"\n")
+    return b"".join(out)

@@ -20,12 +20,21 @@ def test_oracle_matches_reference_on_random_inputs():
     assert "fuzz cpu cases 120 bad 0" in out.stdout, out.stdout[-2000:]
 
 
+# (order, scheme) pairs the 120 cases of seed 78 select, with the minimum number of them the GPU must have CHECKED (not skipped
+# as outside the envelope): the census of this generator is [(q,scheme) -> n] = (0,0) 8, (0,1) 6, (0,2) 14, (1,0) 21, (1,1) 3,
+# (1,2) 19, (2,0) 6, (2,2) 19, (2,4) 19, (2,6) 5; DNA (0,0) 13, (0,1) 6, (3,0) 15, (3,1) 20, (6,0) 12, (6,1) 22, (9,0) 16, (9,1) 16
+FUZZ_MIN_Q = {(0, 0): 6, (0, 1): 4, (0, 2): 11, (1, 0): 17, (1, 1): 2, (1, 2): 15, (2, 0): 4, (2, 2): 15, (2, 4): 15, (2, 6): 4}
+FUZZ_MIN_D = {(0, 0): 10, (0, 1): 4, (3, 0): 12, (3, 1): 16, (6, 0): 9, (6, 1): 17, (9, 0): 12, (9, 1): 12}
+
+
 @pytest.mark.gpu
 def test_gpu_matches_oracle_on_random_inputs():
+    import cases
     import fuzz_parity as fz
     from dsrc_b200 import BlockCompressor, DsrcGpuError
     rng = np.random.default_rng(78)
     checked = 0
+    hit_q, hit_d, unsupported = {}, {}, []
     for it in range(120):
         data, d, q, pr, crc = fz.rand_case(rng)
         chunk = data[:-2] if data.endswith(b"\r\n") else data[:-1]
@@ -41,6 +50,7 @@ def test_gpu_matches_oracle_on_random_inputs():
             got, graw, gcmp = bc.store(chunk)
         except DsrcGpuError as e:
             assert e.code == -5, (it, str(e))          # outside the documented envelope: reported, never a different bitstream
+            unsupported.append(it)
             bc.close()
             continue
         assert (got, graw, gcmp) == (exp, eraw, ecmp), it
@@ -52,4 +62,11 @@ def test_gpu_matches_oracle_on_random_inputs():
             assert bc.read(exp, out_cap=len(data) + 64) == data, it
         bc.close()
         checked += 1
-    assert checked > 90
+        qs, ds = cases.schemes_of(exp, ecmp)
+        hit_q[(q, qs)] = hit_q.get((q, qs), 0) + 1
+        hit_d[(d, ds)] = hit_d.get((d, ds), 0) + 1
+    assert checked >= 105 and len(unsupported) <= 15, (checked, unsupported)
+    for k, n in FUZZ_MIN_Q.items():
+        assert hit_q.get(k, 0) >= n, ("quality", k, hit_q.get(k, 0), n)
+    for k, n in FUZZ_MIN_D.items():
+        assert hit_d.get(k, 0) >= n, ("dna", k, hit_d.get(k, 0), n)

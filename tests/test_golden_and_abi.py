@@ -14,7 +14,7 @@ import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "blocks.json")))
-CASES = {c[0]: c for c in cases.small_cases()}
+CASES = {c[0]: c for c in cases.all_cases()}
 
 
 def sha(b):

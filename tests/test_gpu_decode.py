@@ -11,7 +11,7 @@ import synth
 
 pytestmark = pytest.mark.gpu
 
-CASES = cases.small_cases()
+CASES = cases.all_cases()
 
 
 def _bc(d, q, pr, max_block):

@@ -13,7 +13,7 @@ import synth
 
 pytestmark = pytest.mark.gpu
 
-CASES = cases.small_cases()
+CASES = cases.all_cases()
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blocks.json")
 
 

@@ -189,3 +189,18 @@ def test_cpp_operator_host_paths_need_no_device(tmp_path):
     junk.write_bytes(b"\0" * 100)
     assert L.shim_decompress_file(str(junk).encode(), out, err, 512) != 0
     assert b"Invalid archive" in err.value
+
+
+def test_product_cutter_matches_oracle_including_exact_window_eof():
+    """dsrcgpu_cut_blocks (pure host) == the oracle's restatement of IFastqStreamReader::ReadNextChunk, which
+    test_oracle_vs_ref.py pins to `dsrc c -t1` -- including a chunk window that ends exactly at EOF (src/FastqStream.cpp:66-69)"""
+    from dsrc_b200.operators import cut_blocks
+    cbuf = 1 << 20
+    o = refbind.Oracle()
+    second_start = o.cut(synth.exact_size(3 * cbuf), cbuf)[1][0]
+    files = [synth.exact_size(cbuf), synth.exact_size(cbuf, crlf=True), synth.exact_size(second_start + cbuf), synth.exact_size(cbuf + 1),
+             synth.exact_size(cbuf - 1), synth.illumina(3000, seed=2, regime="full"), b"@r\nA\n+\nI\n", b"@r\r\nA\r\n+\r\nI\r\n"]
+    for data in files:
+        for cb in (cbuf, 1 << 18, 100000):
+            off, ln = cut_blocks(data, cb)
+            assert [(int(a), int(b)) for a, b in zip(off, ln)] == [(int(a), int(b)) for a, b in o.cut(data, cb)], (len(data), cb)

@@ -10,7 +10,7 @@ import refbind
 
 pytestmark = pytest.mark.skipif(not refbind.ref_available(), reason="oracle/_ref not built")
 
-CASES = cases.small_cases()
+CASES = cases.all_cases()
 
 
 @pytest.mark.parametrize("name,data,d,q,pr", CASES, ids=[c[0] for c in CASES])
@@ -103,3 +103,21 @@ def test_changing_title_structure_matches_reference_cli_path(tmp_path):
     dst = tmp_path / "o.dsrc"
     assert refbind.Ref().compress_file(str(src), str(dst), 2, 2, 1, 1, 0) == 0
     assert dst.read_bytes() == refbind.Oracle().compress(big, 2, 2, 1 << 20, 0)
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_cutter_window_ending_exactly_at_eof_matches_reference_cli_path(tmp_path, crlf):
+    """IFastqStreamReader::ReadNextChunk, the `r <= 0` branch (src/FastqStream.cpp:66-69): when a full chunk window ends exactly at
+    EOF the last chunk is the bare carry-over -- its size keeps the final newline (and CR). First window and second window."""
+    import synth
+    cbuf = 1 << 20
+    first = synth.exact_size(cbuf, crlf=crlf)
+    second_start = refbind.Oracle().cut(synth.exact_size(3 * cbuf, crlf=crlf), cbuf)[1][0]
+    for data in (first, synth.exact_size(second_start + cbuf, crlf=crlf), synth.exact_size(cbuf + 1, crlf=crlf), synth.exact_size(cbuf - 1, crlf=crlf)):
+        src = tmp_path / "in.fq"
+        src.write_bytes(data)
+        dst = tmp_path / "o.dsrc"
+        assert refbind.Ref().compress_file(str(src), str(dst), 2, 2, 1, 1, 0) == 0
+        assert dst.read_bytes() == refbind.Oracle().compress(data, 2, 2, cbuf, 0), len(data)
+    blocks = refbind.Oracle().cut(first, cbuf)
+    assert len(blocks) == 2 and blocks[1][0] + blocks[1][1] == len(first)       # the tail chunk keeps the file's last byte
