@@ -309,8 +309,8 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
         CK(cudaMemsetAsync(ctx->tab_mask.p, 0, ctx->tab_mask.cap, s));
         CK(cudaStreamSynchronize(s));                          // once per context: the other slots' streams use the pool too
     }
-    CK(sl.queue.ensure(8));
-    CK(cudaMemsetAsync(sl.queue.p, 0, 8, s));
+    CK(sl.queue.ensure(16));
+    CK(cudaMemsetAsync(sl.queue.p, 0, 16, s));
     CK(sl.tagpool.ensure(tagpool_bytes_per_block() * ctx->tag_ctas));
     if (!rc_q || !rc_d) CK(sl.q0_arena.ensure(ctx->q0_stride * ctx->q0_ctas));
 

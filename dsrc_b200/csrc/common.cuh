@@ -107,7 +107,7 @@ struct Workspace {
     u32 calc_crc;               // CompressionSettings::calculateCrc32
     u8* tab; u64 tab_stride;    // pool of adaptive-row tables of the tile/table model engine (a table is all-zero between blocks)
     u32* tab_mask; u32 tab_count;   // pool bitmap (bit set = in use) and size
-    u32* model_queue;           // [2] next block of the quality / DNA model launch of this batch (zeroed per batch)
+    u32* model_queue;           // [3] next block of the quality / DNA / quality-partition-engine model launch of this batch (zeroed per batch)
     u64* prof;                  // optional: 64 phase cycle counters (clock64 deltas of thread 0 of every CTA), or null
 };
 

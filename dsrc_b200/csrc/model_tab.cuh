@@ -22,6 +22,13 @@
 #define TAB_LONG 24                           // groups longer than this take a whole warp
 #endif
 
+// partition engine (model_part.cuh): state that has to survive the engines' shared-memory union
+#define PART_MAX_BITS 10
+struct PartState {
+    u32 pend[1 << PART_MAX_BITS];             // counting pass: start of every partition in the arena; after the scatter pass: its end
+    u32 d0, d1, a, n;                         // partitions [d0, d1) of the current tile, their span [a, a + n) in the arena
+};
+
 struct TabShared {
     alignas(16) u32 el[2][TT];                // (ctx << 11) | position in tile, ping-pong of the in-tile sort (vector loads)
     u8 sym[TT];
@@ -36,6 +43,8 @@ struct TabShared {
     u32 n_heads[3], n_long, n_touched;
     u32 wv[DSRC_WARPS][4], wcnt[DSRC_WARPS], wflag[DSRC_WARPS];   // scan engine: per-warp aggregates of the segmented scan
     u8 plut[1024];                            // position bucket of every read position when the block's reads have one length
+    u16 pB[DSRC_WARPS][128], pP[DSRC_WARPS][128];   // partition engine: symbol counts of a warp's open run and their exclusive prefix sums
+    PartState part;                           // last: beyond the part of the union the sort engine's scratch overlays (static_assert in rc_model.cu)
 };
 
 // lanes holding the same `bits`-wide digit (replaces match.any, whose cost grows with the number of distinct values)
@@ -104,7 +113,10 @@ __device__ __forceinline__ void tile_sort_pass_t(TabShared& S, u32* scan, const 
 __device__ __forceinline__ void tile_sort_pass(TabShared& S, u32* scan, const u32* src, u32* dst, u32 n, u32 shift, u32 bits)
 {
     switch (bits) {
+    case 1: case 2:
     case 3: tile_sort_pass_t<3>(S, scan, src, dst, n, shift); break;
+    case 4: tile_sort_pass_t<4>(S, scan, src, dst, n, shift); break;
+    case 5: tile_sort_pass_t<5>(S, scan, src, dst, n, shift); break;
     case 6: tile_sort_pass_t<6>(S, scan, src, dst, n, shift); break;
     case 7: tile_sort_pass_t<7>(S, scan, src, dst, n, shift); break;
     case 8: tile_sort_pass_t<8>(S, scan, src, dst, n, shift); break;

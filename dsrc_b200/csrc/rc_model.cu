@@ -96,6 +96,7 @@ struct ModelShared {
         DnaDirectShared dna;                       // shared-memory table engine of the 4-symbol DNA model (model_dna.cuh)
     } u;
 };
+static_assert(offsetof(TabShared, part) >= sizeof(ModelSortShared), "PartState must survive sort_pass / group_scan on an oversize partition");
 #define MODEL_SMEM_QUALITY (offsetof(ModelShared, u) + (sizeof(TabShared) > sizeof(ModelSortShared) ? sizeof(TabShared) : sizeof(ModelSortShared)))
 
 
@@ -116,7 +117,9 @@ struct FetchSorted {
 struct FetchQ {
     typedef u32 Raw;
     static const bool TILE8 = true;
-    __device__ __forceinline__ void tile8(TabShared& S, u32 t0, u32 n);
+    template <bool SCR> __device__ __forceinline__ void tile8x(TabShared& S, u32 t0, u32 n);
+    __device__ __forceinline__ void tile8(TabShared& S, u32 t0, u32 n) { tile8x<false>(S, t0, n); }
+    u32 kmul, kmask;                                  // tile8x<true>: the row index is scrambled, key' = (key * kmul) & kmask (partition engine)
     const u8* q; const u8* pctx; const u8* rank; u32 so, h, bits, M; u32 prev;
     const u8* plut; u32 fixed_len, jpos;              // fixed_len != 0: position bucket from the shared-memory table, indexed by i % len
     u32 ebits, pbits;                                 // tile8: bits per hash slot / per position bucket of the compact row index
@@ -189,7 +192,8 @@ struct FetchD {
 // bits per hash slot as the block's symbol count needs (symbols are dense ranks, their pairwise means are no larger) and
 // log2(rescale) bits of position bucket: the index only has to be injective -- the table is private to the block -- and a
 // 5-symbol block then sorts 16-bit keys (two 8-bit passes, 256 bins) instead of 20-bit ones and keeps its rows within 2 MB.
-__device__ __forceinline__ void FetchQ::tile8(TabShared& S, u32 t0, u32 n)
+template <bool SCR>
+__device__ __forceinline__ void FetchQ::tile8x(TabShared& S, u32 t0, u32 n)
 {
     const u32 p = threadIdx.x * 8, i = t0 + p;
     if (p >= n) return;
@@ -217,6 +221,8 @@ __device__ __forceinline__ void FetchQ::tile8(TabShared& S, u32 t0, u32 n)
         u32 hash;
         if (so == 4 && h == 2) hash = r[4 + k] + r[3 + k] * M1 + a[1 + k] * M2 + a[k] * M3;
         else if (so == 3 && h == 1) hash = r[4 + k] + a[2 + k] * M1 + a[1 + k] * M2;
+        else if (so == 2) hash = r[4 + k] + a[2 + k] * M1;
+        else if (so == 1) hash = r[4 + k];            // SymbolOrder 1: the swap slot is slot 0 and symBuffer stays 0 (QualityEncoder.h:77-89)
         else {
             hash = 0;                                 // y[t] = r[5 + k - t]: symbol t steps back
 #pragma unroll
@@ -225,7 +231,9 @@ __device__ __forceinline__ void FetchQ::tile8(TabShared& S, u32 t0, u32 n)
                 hash |= v << (t * ebits);
             }
         }
-        el[k] = ((hash * MP + pc) << TT_SHIFT) | (p + k);
+        u32 key = hash * MP + pc;
+        if (SCR) key = (key * kmul) & kmask;
+        el[k] = (key << TT_SHIFT) | (p + k);
     }
     ((uint4*)S.el[0])[threadIdx.x * 2] = make_uint4(el[0], el[1], el[2], el[3]);
     ((uint4*)S.el[0])[threadIdx.x * 2 + 1] = make_uint4(el[4], el[5], el[6], el[7]);
@@ -432,6 +440,8 @@ __device__ void group_scan(ModelShared& S, const u64* sorted, u32* longq, u64* t
     PROF_MARK(prof_base + 4);
 }
 
+#include "model_part.cuh"
+
 // Pool of adaptive-row tables shared by every model CTA of the context (all slots): bit set = table in use. A table is
 // all-zero whenever it is in the pool. The pool holds one table per CTA that can be resident (4 per SM), so a CTA never
 // waits unless tables are held by CTAs of another launch that are still running -- which then finish and release.
@@ -455,7 +465,9 @@ __device__ u32 tab_acquire(u32* mask, u32 count)
 }
 __device__ void tab_release(u32* mask, u32 id) { atomicAnd(&mask[id >> 5], ~(1u << (id & 31))); }
 
-template <bool QUALITY>
+// PART: the launch that runs the partition engine (blocks whose quality scheme has rows of 32+ symbols); the other launch skips
+// those blocks. Two kernels instead of one so that each keeps its own register allocation.
+template <bool QUALITY, bool PART>
 __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 {
     extern __shared__ __align__(16) u8 model_smem[];       // sizeof(ModelShared) > 48 KiB: opt-in dynamic shared memory
@@ -469,7 +481,7 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 
     // blocks are handed out by a per-launch counter (the CTAs of a launch finish together whatever the blocks cost); the
     // adaptive-row table of the tile/table engine is taken from the context-wide pool on first need and returned at the end
-    u32* const queue = ws.model_queue + (QUALITY ? 0 : 1);
+    u32* const queue = ws.model_queue + (PART ? 2 : QUALITY ? 0 : 1);
     u8* tab = nullptr;
     auto next_block = [&]() -> u32 {
         __syncthreads();
@@ -491,6 +503,13 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
                 st.q_scheme = (u8)sc;
                 if (sc == 255) S.ok = 0;                        // SchemeNone: just the scheme byte
                 else if (!quality_cfg(ws.qua_order, sc, S.cfg)) { S.ok = 0; st.status = ST_UNSUPPORTED; }
+                else {
+                    // rows of 32+ symbols belong to the partition engine's launch (first), unless its per-warp 16-bit counters cannot
+                    // hold the block (multi-MB blocks) or it gave the block back (st.pad[0])
+                    const bool part = S.cfg.alpha > 16 && st.q_total < DSRC_WARPS * 65000u;
+                    if (PART) { if (part) st.pad[0] = 0; else S.ok = 0; }
+                    else if (part && !st.pad[0]) S.ok = 0;
+                }
                 S.M = st.q_total;
             } else {
                 u32 sc = st.d_count == 0 ? 255u : (st.d_count <= 4 ? 0u : 1u);
@@ -516,7 +535,8 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
         u8* pc = (u8*)bufB;
         u32 fixed_len = 0;
         const bool tabpath = cfg.alpha <= 16 && ws.tab != nullptr;
-        if (QUALITY && tabpath && st.min_len == st.max_len && st.max_len > 0 && st.max_len <= 1024) {
+        const bool partpath = QUALITY && PART;
+        if (QUALITY && (tabpath || partpath) && st.min_len == st.max_len && st.max_len > 0 && st.max_len <= 1024) {
             // one read length in the block: position bucket j * rescale / len (TTranslationalQualityEncoder::Encode :307) from a small table
             fixed_len = st.max_len;
             for (u32 j = tid; j < fixed_len; j += DSRC_CTA) TS.plut[j] = (u8)(j * cfg.rescale / fixed_len);
@@ -530,6 +550,18 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
             }
             __syncthreads();
         }
+        if (partpath && PART) {
+            // ---- partition engine (model_part.cuh): 32 / 64 / 128-symbol quality rows, table-free. It runs BEFORE the other launch
+            // and hands a block it cannot take (a partition beyond its 16-bit offsets: one very hot context) over through st.pad[0]
+            if (QUALITY) {
+                FetchQ f; f.q = ws.qcat + d.sym_base; f.pctx = pc; f.rank = S.rank; f.so = cfg.sym_order; f.h = cfg.sym_order / 2; f.bits = cfg.bits; f.prev = 0; f.M = M; f.plut = TS.plut; f.fixed_len = fixed_len; f.jpos = 0;
+                f.ebits = 1; while ((1u << f.ebits) < st.q_count) ++f.ebits;
+                f.pbits = cfg.rescale > 8 ? cfg.bits : 3;
+                if (!part_engine(S, f, M, f.pbits + cfg.sym_order * f.ebits, cfg.alpha, f.ebits, bufA, bufB, trip, ws, prof_t, 32) && tid == 0) st.pad[0] = 1;
+            }
+            continue;
+        }
+        if (PART) continue;
         if (!QUALITY && cfg.alpha == 4 && cfg.key_bits <= 12) {
             // ---- whole table in shared memory (model_dna.cuh)
             dna_direct_engine(S.u.dna, ws.dcat + d.sym_base, M, cfg.ord, trip);
@@ -709,11 +741,17 @@ static u32 model_grid(const Workspace& ws, u32 max_ctas)
 }
 static void model_smem_optin()
 {
-    cudaFuncSetAttribute(k_model<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
-    cudaFuncSetAttribute(k_model<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
+    cudaFuncSetAttribute(k_model<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
+    cudaFuncSetAttribute(k_model<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
+    cudaFuncSetAttribute(k_model<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ModelShared));
 }
-void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<true><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride); }
-void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
+void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride)
+{
+    model_smem_optin();
+    k_model<true, true><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride);
+    k_model<true, false><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride);
+}
+void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false, false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
 cudaError_t rc_init_device() { k_rcp_lut<<<65536 / 256, 256>>>(); return cudaDeviceSynchronize(); }
 void launch_rc_encode(const Workspace& ws, cudaStream_t s)
 {

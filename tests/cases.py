@@ -108,6 +108,11 @@ def scale_cases():
     c.append(("scale_truncated_d0_q0", synth.block_scale(n_levels=38, seed=112, q_lo=3, tail_frac=0.7, tail_max=80), 0, 0, 0, (1, 0)))
     c.append(("scale_truncated_varlen_d6_q0", synth.block_scale(n_reads=1600, n_levels=38, seed=113, q_lo=3, tail_frac=0.7, tail_max=30, varlen=True), 6, 0, 0, (1, 0)))
     c.append(("scale_rle_d6_q0", synth.block_scale(n_levels=30, sticky=True, seed=114, q_lo=3), 6, 0, 0, (2, 0)))
+    # hot contexts in the large-alphabet models: a few contexts hold thousands (the partition engine's oversize partitions) or tens of
+    # thousands of symbols (its fallback to the sort engine, with TSymbolCoderRC::Rescale firing inside 32- and 64-symbol rows)
+    c.append(("scale_hot64_d6_q2", synth.skewed(3000, seed=115, levels=tuple(range(2, 42))), 6, 2, 0, (6, 0)))
+    c.append(("scale_hot32_rescale_d6_q2", synth.skewed(5000, seed=116, levels=tuple(range(7, 31))), 6, 2, 0, (5, 0)))
+    c.append(("scale_hot64_rescale_d3_q1", synth.skewed(5000, seed=117, p_major=0.99, levels=tuple(range(2, 42))), 3, 1, 0, (2, 0)))
     return c
 
 

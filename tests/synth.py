@@ -112,13 +112,13 @@ def mixed_titles(n_reads, length=50, seed=3):
     return b"".join(lines)
 
 
-def skewed(n_reads, length=150, seed=8, p_major=0.97):
+def skewed(n_reads, length=150, seed=8, p_major=0.97, levels=(2, 12, 23, 37)):
     """almost-constant bases and qualities: a handful of contexts hold tens of thousands of symbols each, so the
     adaptive rows hit TSymbolCoderRC::Rescale (src/SymbolCoderRC.h:69-73) several times inside one block."""
     rng = np.random.default_rng(seed)
     seq = np.where(rng.random((n_reads, length)) < p_major, ord("A"), BASES[rng.integers(0, 4, size=(n_reads, length))]).astype(np.uint8)
-    lv = np.array([2, 12, 23, 37], dtype=np.uint8) + 33
-    qual = np.where(rng.random((n_reads, length)) < p_major, ord("I"), lv[rng.integers(0, 4, size=(n_reads, length))]).astype(np.uint8)
+    lv = np.array(levels, dtype=np.uint8) + 33
+    qual = np.where(rng.random((n_reads, length)) < p_major, ord("I"), lv[rng.integers(0, len(lv), size=(n_reads, length))]).astype(np.uint8)
     return b"".join(b"@SK.%d 1:N:0\n" % (i + 1) + seq[i].tobytes() + b"\n+\n" + qual[i].tobytes() + b"\n" for i in range(n_reads))
 
 

@@ -53,7 +53,7 @@ tot = L.dsrcgpu_last_call_ms(ctx)
 print("blocks %d  bytes %.2f GB  call %.1f ms  -> %.2f GB/s" % (n, nbytes / 1e9, tot, nbytes / tot / 1e6))
 for i in range(k):
     print("  %-14s %8.2f ms  %3d launches" % (names[i].decode(), ms[i], ln[i]))
-lab = {0: "q.pass1", 1: "q.pass2+", 2: "q.heads", 3: "q.scan_short", 4: "q.scan_long", 8: "d.pass1", 9: "d.pass2+", 10: "d.heads", 11: "d.scan_short", 12: "d.scan_long", 16: "q.tab ctx", 17: "q.tab sort", 18: "q.tab heads", 19: "q.tab short", 20: "q.tab long", 21: "q.tab store", 22: "q.tab clean", 24: "d.tab ctx", 25: "d.tab sort", 26: "d.tab heads", 27: "d.tab short", 28: "d.tab long", 29: "d.tab store", 30: "d.tab clean", 14: "d.direct", 7: "q.direct", 40: "qd rounds(count x1e6)", 41: "qd steps(x1e6)", 42: "qd fallbacks(x1e6)"}
+lab = {0: "q.pass1", 1: "q.pass2+", 2: "q.heads", 3: "q.scan_short", 4: "q.scan_long", 8: "d.pass1", 9: "d.pass2+", 10: "d.heads", 11: "d.scan_short", 12: "d.scan_long", 16: "q.tab ctx", 17: "q.tab sort", 18: "q.tab heads", 19: "q.tab short", 20: "q.tab long", 21: "q.tab store", 22: "q.tab clean", 24: "d.tab ctx", 25: "d.tab sort", 26: "d.tab heads", 27: "d.tab short", 28: "d.tab long", 29: "d.tab store", 30: "d.tab clean", 14: "d.direct", 7: "q.direct", 32: "q.part count", 33: "q.part scatter", 34: "q.part load+sort", 35: "q.part rows", 36: "q.part store", 38: "q.part oversize", 43: "q.part over short", 44: "q.part over long"}
 for i in range(64):
     if ph[i]:
         print("  phase %-14s %10.1f Mcycles (sum over CTAs)" % (lab.get(i, str(i)), ph[i] / 1e6))
