@@ -190,88 +190,65 @@ __device__ bool part_engine(ModelShared& MS, F f, u32 M, u32 key_bits, u32 N, u3
     TabShared& S = MS.u.tab;
     PartState& PS = S.part;
     const u32 tid = threadIdx.x;
+    // (a warp-private form of passes 0/1 -- every warp its own eighth of the block, per-(warp, partition) offsets, no CTA barrier --
+    // was measured 20 % SLOWER on B200: the partitions are then written in eight interleaved pieces and pass 2 waits longer for them)
     // partitions of about 100 elements (a warp's tile holds two or three), at most 2^PART_MAX_BITS of them and never more than keys
     u32 pb = key_bits > 13 ? key_bits - 10 : 3;       // a warp's counting sort has 2^10 counters: at most 10 key bits below the partition
     while (pb < PART_MAX_BITS && pb < key_bits && (M >> pb) > 128) ++pb;
     const u32 bins = 1u << pb, lowbits = key_bits - pb;
     f.kmul = PART_MUL; f.kmask = (1u << key_bits) - 1;
 
-    // ---- pass 0: elements per (warp, partition). Every warp owns a contiguous eighth of the block and nothing below needs a CTA
-    // barrier inside the loops: 16-bit counters (a warp's eighth is < 2^16 symbols, checked by the caller), packed two per word
-    const u32 w = warp_id(), ln = lane_id(), lt = (1u << ln) - 1;
-    const u32 seg = (((M + DSRC_WARPS - 1) / DSRC_WARPS) + PW - 1) & ~(u32)(PW - 1);
-    const u32 wb = min(M, w * seg), we = min(M, wb + seg);
-    u16* cnt = S.x.H + w * bins;                       // then: rel[w][d] = elements of partition d in the warps before w, running
-    for (u32 i = tid; i < DSRC_WARPS * bins / 2; i += DSRC_CTA) ((u32*)S.x.H)[i] = 0;
+    // ---- pass 0: elements per partition
+    for (u32 d = tid; d < bins; d += DSRC_CTA) PS.pend[d] = 0;
     __syncthreads();
-    for (u32 c = wb; c < we; c += PW) {
-        const u32 t0 = c - w * PW;                     // so that t0 + threadIdx.x * 8 is this lane's first symbol
-        if (ln == 0 && c + PW < we) asm volatile("prefetch.global.L2 [%0];" :: "l"(f.q + c + PW));
-        f.template tile8x<true>(S, t0, we - t0);
-        if (c + ln * 8 < we) {
+    for (u32 t0 = 0; t0 < M; t0 += TT) {
+        const u32 n = min((u32)TT, M - t0);
+        f.prefetch(t0 + TT, tid);
+        f.template tile8x<true>(S, t0, n);
+        const u32 p0 = tid * 8;
+        if (p0 < n) {
             const uint4 a = ((const uint4*)S.el[0])[tid * 2], b = ((const uint4*)S.el[0])[tid * 2 + 1];
             const u32 e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             u32 run = 0, dprev = e[0] >> (TT_SHIFT + lowbits);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {             // neighbours may share a partition: one atomic per run
-                const bool in = c + ln * 8 + k < we;
+                const bool in = p0 + k < n;
                 const u32 d = e[k] >> (TT_SHIFT + lowbits);
                 if (in && d == dprev) ++run;
-                else { if (run) atomicAdd((u32*)cnt + (dprev >> 1), run << ((dprev & 1) * 16)); run = in ? 1u : 0u; dprev = d; }
+                else { if (run) atomicAdd(&PS.pend[dprev], run); run = in ? 1u : 0u; dprev = d; }
             }
-            if (run) atomicAdd((u32*)cnt + (dprev >> 1), run << ((dprev & 1) * 16));
+            if (run) atomicAdd(&PS.pend[dprev], run);
         }
     }
     __syncthreads();
-    bool big = false;
     {
         const u32 per = bins > DSRC_CTA ? bins / DSRC_CTA : 1u, d0 = tid * per;
-        u32 sum = 0;
-        if (d0 < bins) for (u32 k = 0; k < per; ++k) for (u32 ww = 0; ww < DSRC_WARPS; ++ww) sum += S.x.H[ww * bins + d0 + k];
+        u32 sum = 0, c[4];
+        if (d0 < bins) for (u32 k = 0; k < per; ++k) { c[k] = PS.pend[d0 + k]; sum += c[k]; }
         u32 total, run = block_excl_sum(sum, MS.scan, &total);
-        if (d0 < bins) for (u32 k = 0; k < per; ++k) {
-            u32 r = 0;
-            for (u32 ww = 0; ww < DSRC_WARPS; ++ww) { const u32 cc = S.x.H[ww * bins + d0 + k]; S.x.H[ww * bins + d0 + k] = (u16)r; r += cc; }
-            big |= r > 0xFFFFu;                         // a partition the 16-bit running offsets cannot address: one very hot context
-            PS.pend[d0 + k] = run; run += r;
-        }
+        if (d0 < bins) for (u32 k = 0; k < per; ++k) { PS.pend[d0 + k] = run; run += c[k]; }
     }
-    if (__syncthreads_or(big)) return false;
+    __syncthreads();
     PROF_MARK(prof_base + 0);
 
-    // ---- pass 1: the same symbols again, appended to their partitions in the arena (stable: warps own ascending eighths, rows and
-    // lanes are taken in order)
-    for (u32 c = wb; c < we; c += PW) {
-        const u32 t0 = c - w * PW;
-        if (ln == 0 && c + PW < we) asm volatile("prefetch.global.L2 [%0];" :: "l"(f.q + c + PW));
-        f.template tile8x<true>(S, t0, we - t0);
-        __syncwarp();
-        const u32* slice = S.el[0] + w * PW;
-#pragma unroll 2
-        for (u32 r = 0; r < PW / 32; ++r) {
-            const u32 i = r * 32 + ln; const bool valid = c + i < we;
-            const u32 e = slice[i], d = e >> (TT_SHIFT + lowbits), p = e & (TT - 1);
-            const u32 vm = __ballot_sync(FULL, valid);
-            if (!vm) break;
-            const u32 peers = valid ? __match_any_sync(vm, d) : 0u;
-            const u32 pos = valid ? (u32)cnt[d] + __popc(peers & lt) : 0u;
-            __syncwarp();
-            if (valid) {
-                if ((__ffs(peers) - 1) == (int)ln) cnt[d] += (u16)__popc(peers);
-                arena[PS.pend[d] + pos] = ((u64)(e >> TT_SHIFT) << 40) | ((u64)S.sym[p] << 32) | (t0 + p);
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    {   // partition starts -> partition ends
-        const u32 per = bins > DSRC_CTA ? bins / DSRC_CTA : 1u, d0 = tid * per;
-        u32 nx[4];
-        if (d0 < bins) for (u32 k = 0; k < per; ++k) nx[k] = d0 + k + 1 < bins ? PS.pend[d0 + k + 1] : M;
+    // ---- pass 1: every tile sorted by partition in shared memory (one stable radix pass), then appended to the partitions in the arena
+    for (u32 t0 = 0; t0 < M; t0 += TT) {
+        const u32 n = min((u32)TT, M - t0);
+        f.prefetch(t0 + TT, tid);
+        f.template tile8x<true>(S, t0, n);
         __syncthreads();
-        if (d0 < bins) for (u32 k = 0; k < per; ++k) PS.pend[d0 + k] = nx[k];
+        tile_sort_pass(S, MS.scan, S.el[0], S.el[1], n, TT_SHIFT + lowbits, pb);
+        const u32* sorted = S.el[1];
+        const u16* HE = S.x.H + (DSRC_WARPS - 1) * bins;      // after the scatter: end of every partition's slice of the sorted tile
+        for (u32 j = tid; j < n; j += DSRC_CTA) {
+            const u32 e = sorted[j], d = e >> (TT_SHIFT + lowbits), p = e & (TT - 1);
+            const u32 ts = d ? HE[d - 1] : 0u;
+            arena[PS.pend[d] + (j - ts)] = ((u64)(e >> TT_SHIFT) << 40) | ((u64)S.sym[p] << 32) | (t0 + p);
+        }
+        __syncthreads();
+        for (u32 d = tid; d < bins; d += DSRC_CTA) PS.pend[d] += (u32)HE[d] - (d ? (u32)HE[d - 1] : 0u);
+        __syncthreads();
     }
-    __syncthreads();
     PROF_MARK(prof_base + 1);
 
     // ---- pass 2: consecutive partitions are grouped into warp tiles (<= PW elements, <= 10 significant key bits); a partition that
@@ -292,11 +269,19 @@ __device__ bool part_engine(ModelShared& MS, F f, u32 M, u32 key_bits, u32 N, u3
     __syncthreads();
     {
         const u32 ng = PS.n;
+        u32 gn = 0;                                    // the tile after this one: taken early so that its span of the arena is on its way
+        if (lane_id() == 0) gn = atomicAdd(&PS.a, 1u);
+        gn = __shfl_sync(FULL, gn, 0);
         for (;;) {
-            u32 g = 0;
-            if (lane_id() == 0) g = atomicAdd(&PS.a, 1u);
-            g = __shfl_sync(FULL, g, 0);
+            const u32 g = gn;
             if (g >= ng) break;
+            if (lane_id() == 0) gn = atomicAdd(&PS.a, 1u);
+            gn = __shfl_sync(FULL, gn, 0);
+            if (gn < ng && !(glist[gn] & 0x8000u)) {
+                const u32 p0 = glist[gn], p1 = glist[gn + 1] & 0x7FFFu;
+                const u32 pa = p0 ? PS.pend[p0 - 1] : 0u, pn = PS.pend[p1 - 1] - pa;
+                if (lane_id() * 16 < pn) asm volatile("prefetch.global.L2 [%0];" :: "l"(arena + pa + lane_id() * 16));
+            }
             const u32 d0 = glist[g];
             if (d0 & 0x8000u) continue;
             const u32 d1 = glist[g + 1] & 0x7FFFu;
