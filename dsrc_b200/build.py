@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "libdsrc_b200.so")
 def build(force=False, verbose=False):
     srcs = [os.path.join(HERE, "csrc", s) for s in SRCS]
     deps = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + \
-        [os.path.join(os.path.dirname(HERE), "include", "dsrc_b200.h")]
+        [os.path.join(os.path.dirname(HERE), "include", h) for h in ("dsrc_b200.h", "dsrc_b200_bench.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -4,6 +4,7 @@
 // threads each owning a BlockCompressor, the block queue is cut into batches; each batch is laid out in HBM
 // (dense per-batch arrays + persistent per-CTA arenas) and pushed through the per-block kernels on a stream.
 #include "../../include/dsrc_b200.h"
+#include "../../include/dsrc_b200_bench.h"
 #include "common.cuh"
 #include "kernels.h"
 #include <string>
@@ -368,7 +369,26 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         CK(ctx->cursor.ensure(8));
         CK(cudaMemsetAsync(ctx->cursor.p, 0, 8, ctx->slots[0].stream));
     }
-    const u32 nb = (n + ctx->max_inflight - 1) / ctx->max_inflight;
+    // batch schedule. Resident input: uniform batches. Host buffers: the first and the last batches are small (1/8, 1/8, 1/4, 1/2 of a
+    // full batch, mirrored at the end), so the first kernels start after a few milliseconds of H2D instead of a whole 2 GiB batch and
+    // the last output copy is short -- the copy pipeline's fill and drain are what a host-buffer call pays on top of max(copy, compute)
+    std::vector<u32> bfirst;
+    {
+        const u32 full = ctx->max_inflight;
+        u32 ramp[4] = {std::max(1u, full / 8), std::max(1u, full / 8), std::max(1u, full / 4), std::max(1u, full / 2)};
+        const u32 rsum = ramp[0] + ramp[1] + ramp[2] + ramp[3];
+        u32 pos = 0;
+        if (!on_device && full >= 64 && n >= 2 * rsum + full && !getenv("DSRCGPU_NO_RAMP")) {
+            for (int k = 0; k < 4; ++k) { bfirst.push_back(pos); pos += ramp[k]; }
+            while (n - pos - rsum >= full) { bfirst.push_back(pos); pos += full; }
+            if (n - pos > rsum) { bfirst.push_back(pos); pos = n - rsum; }
+            for (int k = 3; k >= 0; --k) { bfirst.push_back(pos); pos += ramp[k]; }
+        } else {
+            for (; pos < n; pos += full) bfirst.push_back(pos);
+        }
+        bfirst.push_back(n);
+    }
+    const u32 nb = (u32)bfirst.size() - 1;
     u64 out_pos = 0;
     u32 retired = 0;
     int rc = DSRCGPU_OK;
@@ -418,7 +438,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
             if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = DSRCGPU_E_CUDA; break; }
             sl.busy = false;
         }
-        const u32 first = b * ctx->max_inflight, cnt = std::min(ctx->max_inflight, n - first);
+        const u32 first = bfirst[b], cnt = bfirst[b + 1] - first;
         sl.first = first; sl.cnt = cnt; sl.batch = b;
         sl.offs.resize(cnt);
         const u8* d_in; u8* d_out; u64 batch_out_base = 0, batch_out_cap;

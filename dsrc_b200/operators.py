@@ -222,25 +222,76 @@ class DsrcCompressorMT:
         return archive, (my_off, payload)
 
 
+def dist_gather_sizes(my_sizes, device):
+    """the one exchange of the multi-rank path (src/DsrcFile.cpp:142: one footer with every block's size): all-gather of the ranks'
+    uint32 block sizes over the default torch.distributed group -- NCCL when `device` is the rank's GPU, gloo when it is "cpu"."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    n = torch.tensor([len(my_sizes)], dtype=torch.int64, device=device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    mx = max(1, max(int(x) for x in ns))
+    pad = torch.zeros(mx, dtype=torch.int64, device=device)
+    if len(my_sizes):
+        pad[:len(my_sizes)] = torch.from_numpy(np.asarray(my_sizes).astype(np.int64)).to(device)
+    outs = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return [o[:int(k)].cpu().numpy().astype(np.uint32) for o, k in zip(outs, ns)]
+
+
+def write_archive_sharded(path, archive, my_slice, rank, barrier=None):
+    """DsrcFileWriter as N ranks see it (src/DsrcFile.cpp:75-170; the ordered writer of src/DsrcIo.cpp:19-89 becomes offsets):
+    rank 0 writes the 40-byte header and the footer, EVERY rank pwrites its compressed blocks at 40 + (bytes of the ranks before it).
+    `archive` / `my_slice` are what DsrcCompressorMT.process returned on this rank."""
+    import os
+    my_off, payload = my_slice
+    if rank == 0:
+        fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+        if isinstance(archive, tuple):
+            header, footer = archive
+            footer_off = struct.unpack(">Q", header[8:16])[0]
+            os.pwrite(fd, header, 0)
+            os.pwrite(fd, footer, footer_off)
+            os.pwrite(fd, payload, my_off)
+        else:
+            os.pwrite(fd, archive, 0)
+        os.close(fd)
+    if barrier is not None:
+        barrier()                      # the file exists before the other ranks open it
+    if rank != 0:
+        fd = os.open(path, os.O_RDWR)
+        os.pwrite(fd, payload, my_off)
+        os.close(fd)
+    if barrier is not None:
+        barrier()
+
+
 class DsrcDecompressorMT:
     """IDsrcOperator::Process for decompression (src/DsrcOperator.cpp:397-525) on an in-memory archive."""
 
-    def __init__(self, device=0):
-        self.device = device
+    def __init__(self, device=0, rank=0, world=1):
+        self.device, self.rank, self.world = device, rank, world
 
     def process(self, archive, max_inflight_blocks=0):
+        """single rank: the whole FASTQ. With several ranks (BASELINE configs[4]) every rank reads the footer, takes a contiguous block
+        range balanced by compressed bytes and returns (offset of its part in the FASTQ file, bytes): the output offsets need nothing
+        but every block's chunkSize (bytes 12..15 of its header, src/BlockCompressor.cpp:302-308), so there is no exchange at all."""
         offs, sizes, st = read_archive_index(archive)
+        mv = memoryview(archive)
+        out_sizes = np.array([struct.unpack(">I", mv[int(o) + 12:int(o) + 16])[0] + 1 for o in offs], dtype=np.uint64)
+        b0, b1 = shard_ranges(sizes, self.world)[self.rank]
+        my_off = int(out_sizes[:b0].sum())
+        if b1 <= b0:
+            return b"" if self.world == 1 else (my_off, b"")
         bc = BlockCompressor(st["quality_offset"], st["plus_repetition"], st["dna_order"], st["quality_order"],
                              max_block_bytes=1 << 20, max_inflight_blocks=max_inflight_blocks, device=self.device, calc_crc32=st["calc_crc32"])
         try:
-            total = 0
-            for o in offs:            # chunkSize + 1 of every block (BlockCompressor.cpp:302-308)
-                o = int(o)
-                total += struct.unpack(">I", archive[o + 12:o + 16])[0] + 1
-            parts = bc.read_many(archive, offs, sizes, total + 64)
+            parts = bc.read_many(archive, offs[b0:b1], sizes[b0:b1], int(out_sizes[b0:b1].sum()) + 64)
         finally:
             bc.close()
-        return b"".join(parts)
+        data = b"".join(parts)
+        return data if self.world == 1 else (my_off, data)
 
 
 class DsrcModule:

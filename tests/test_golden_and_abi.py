@@ -47,7 +47,7 @@ def test_oracle_matches_golden_archives(name):
 
 
 def test_abi_exports_every_declared_symbol():
-    hdr = open(os.path.join(ROOT, "include", "dsrc_b200.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "dsrc_b200.h")).read() + open(os.path.join(ROOT, "include", "dsrc_b200_bench.h")).read()
     names = sorted(set(re.findall(r"\b(dsrcgpu_[a-z0-9_]+)\s*\(", hdr)))
     assert len(names) >= 15
     lib_path = os.path.join(ROOT, "dsrc_b200", "libdsrc_b200.so")

@@ -102,37 +102,42 @@ def test_device_synth_matches_host_twin():
     from dsrc_b200 import _lib
     L = _lib.lib()
     bc = _bc(6, 2, 0, 1 << 18)
-    for profile in (0, 1):
+    for profile in (0, 1, 2):
         n = 3000
-        cap = n * 372
+        cap = n * (372 if profile < 2 else 1300)
         d = torch.empty(cap, dtype=torch.uint8, device="cuda")
         nb = C.c_uint64()
         assert L.dsrcgpu_synth_fastq_device(bc.h, profile, 99, 12345, n, C.c_void_p(d.data_ptr()), cap, C.byref(nb)) == 0
         h = np.empty(cap, dtype=np.uint8)
         nb2 = C.c_uint64()
         assert L.dsrcgpu_synth_fastq_host(profile, 99, 12345, n, h.ctypes.data_as(C.c_void_p), cap, C.byref(nb2)) == 0
-        assert nb.value == nb2.value == cap
-        assert d.cpu().numpy().tobytes() == h.tobytes()
+        assert nb.value == nb2.value and (profile == 2 or nb.value == cap)
+        assert d[:nb.value].cpu().numpy().tobytes() == h[:nb.value].tobytes()
     bc.close()
 
 
 def test_bench_shape_blocks_match_oracle():
-    """the bench workload's generator (profile 0 and 1), 256 KB blocks, -d2 -q2: every block of a 40-block sample"""
+    """the bench workloads' generators at 256 KB blocks, every block of a 40-block sample: Illumina shape (profile 0 and 1) at -d2 -q2,
+    454 / Ion shape (profile 2: variable lengths, IUPAC codes -> 8-symbol order-7 DNA + 64-symbol quality) at -d3 -q2, and the
+    binned Illumina shape at -d0 -q0 (RLE quality) -- BASELINE configs[1] and configs[2]"""
     import ctypes as C
     from dsrc_b200 import _lib
     L = _lib.lib()
-    for profile in (0, 1):
-        n = 28000
-        h = np.empty(n * 372, dtype=np.uint8)
+    for profile, d, q in ((0, 6, 2), (1, 6, 2), (2, 9, 2), (0, 0, 0)):
+        n = 28000 if profile < 2 else 14000
+        h = np.empty(n * (372 if profile < 2 else 1300), dtype=np.uint8)
         nb = C.c_uint64()
         L.dsrcgpu_synth_fastq_host(profile, 99, 0, n, h.ctypes.data_as(C.c_void_p), h.size, C.byref(nb))
-        big = h.tobytes()
-        ora = refbind.Oracle(33, 0, 6, 2)
+        big = h[:nb.value].tobytes()
+        ora = refbind.Oracle(33, 0, d, q)
         blocks = ora.cut(big, 1 << 18)
-        bc = _bc(6, 2, 0, 1 << 18)
+        assert len(blocks) >= 40
+        bc = _bc(d, q, 0, 1 << 18)
         got, _, _ = bc.store_many(big, [b[0] for b in blocks], [b[1] for b in blocks])
         for i, (o, l) in enumerate(blocks):
             assert got[i] == ora.store(big[o:o + l])[0], (profile, i)
+        dec = bc.read_many(b"".join(got), np.cumsum([0] + [len(g) for g in got[:-1]]).tolist(), [len(g) for g in got], out_cap=len(big) + 64)
+        assert b"".join(dec) == big, profile
         bc.close()
 
 
