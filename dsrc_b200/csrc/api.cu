@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
+#include <time.h>
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DSRCGPU_E_CUDA; } } while (0)
 
@@ -31,9 +33,10 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_DEC_TAGS, K_DEC_Q, K_DEC_D, K_DEC_ASM, K_CRC, K_NUM };
+enum { K_COUNT, K_PARSE, K_PREP, K_TAGS, K_MODEL_Q, K_MODEL_D, K_RC, K_Q0, K_D0, K_SIZES, K_GATHER, K_DECODE, K_DEC_TAGS, K_DEC_Q, K_DEC_D, K_DEC_ASM, K_CRC, K_H2D, K_D2H, K_NUM };
 static const char* K_NAMES[K_NUM] = {"count_lines", "parse", "preprocess", "tags", "model_quality", "model_dna", "rc_encode",
-                                     "q0_quality", "d0_dna", "meta_sizes", "gather", "decode_probe", "decode_tags", "decode_quality", "decode_dna", "decode_assemble", "crc32"};
+                                     "q0_quality", "d0_dna", "meta_sizes", "gather", "decode_probe", "decode_tags", "decode_quality", "decode_dna", "decode_assemble", "crc32",
+                                     "copy_h2d", "copy_d2h"};      // the last two: payload copies of the host-buffer calls (not kernels)
 #define MAX_SLOTS 8
 
 // One in-flight batch of blocks: its own stream, workspace and pinned staging. The scheduler keeps several slots busy so
@@ -44,7 +47,7 @@ struct Slot {
     DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
     DevBuf elem_a, elem_b, tagpool, q0_arena, queue;        // per-CTA arenas of the persistent kernels, block queue counters
     BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
-    cudaEvent_t ev_results = nullptr, ev_sizes = nullptr;
+    cudaEvent_t ev_results = nullptr, ev_sizes = nullptr, ev_probe = nullptr;
     bool busy = false; u32 first = 0, cnt = 0, batch = 0;
     Workspace ws{};                                          // of the batch in flight (re-used if its output staging has to grow)
     std::vector<u64> offs;
@@ -60,8 +63,9 @@ struct Slot {
         h_desc = nullptr; h_result = nullptr; h_probe = nullptr; h_cap = 0;
         if (ev_results) cudaEventDestroy(ev_results);
         if (ev_sizes) cudaEventDestroy(ev_sizes);
+        if (ev_probe) cudaEventDestroy(ev_probe);
         if (stream) cudaStreamDestroy(stream);
-        ev_results = ev_sizes = nullptr; stream = nullptr;
+        ev_results = ev_sizes = ev_probe = nullptr; stream = nullptr;
     }
 };
 
@@ -146,7 +150,8 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
         Slot& sl = ctx->slots[i];
         if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&sl.ev_results, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&sl.ev_sizes, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&sl.ev_sizes, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sl.ev_probe, cudaEventDisableTiming) != cudaSuccess) {
             for (int k = 0; k <= i; ++k) ctx->slots[k].release();
             delete ctx; return DSRCGPU_E_CUDA;
         }
@@ -242,8 +247,10 @@ static int status_to_error(dsrcgpu_ctx* ctx, u32 status, u32 blk)
 // Enqueues one batch of blocks on its slot's stream: layout probe (one short host sync), then every per-block kernel and the
 // result read-back, all asynchronous. d_in / d_out are device pointers; with `cursor` the dense output continues where the
 // previous batch ended (device-resident output), else the batch starts at out_base of its own staging buffer.
+// `idle` is called over and over while the host waits for the layout probe (i.e. for this batch's input copy): the scheduler uses it
+// to retire batches that finish meanwhile, so that their output copies start at once and run beside this input copy.
 static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* blk_len, const u32* blk_tagcap, u32 n,
-                         u8* d_out, u64 out_base, u64 out_cap, u64* cursor, cudaEvent_t wait_sizes)
+                         u8* d_out, u64 out_base, u64 out_cap, u64* cursor, cudaEvent_t wait_sizes, const std::function<int()>& idle)
 {
     int rc = ensure_host(ctx, sl, n);
     if (rc) return rc;
@@ -271,7 +278,15 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
     { KTimer t(ctx, &sl, K_COUNT); launch_count_lines(ws, s); }
     CK(cudaMemcpyAsync(sl.h_probe, sl.probe.p, sizeof(BlockProbe) * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(sl.ev_probe, s));
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(sl.ev_probe);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { ctx->err = std::string("layout probe: ") + cudaGetErrorString(q); return DSRCGPU_E_CUDA; }
+        if (idle) { const int r = idle(); if (r) return r; }
+        const struct timespec ts = {0, 20000};
+        nanosleep(&ts, nullptr);
+    }
 
     u64 lines = 0, recs = 0, syms = 0, ftab = 0, streams = 0;
     for (u32 i = 0; i < n; ++i) {
@@ -369,25 +384,12 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         CK(ctx->cursor.ensure(8));
         CK(cudaMemsetAsync(ctx->cursor.p, 0, 8, ctx->slots[0].stream));
     }
-    // batch schedule. Resident input: uniform batches. Host buffers: the first and the last batches are small (1/8, 1/8, 1/4, 1/2 of a
-    // full batch, mirrored at the end), so the first kernels start after a few milliseconds of H2D instead of a whole 2 GiB batch and
-    // the last output copy is short -- the copy pipeline's fill and drain are what a host-buffer call pays on top of max(copy, compute)
+    // batch schedule: uniform batches. (Measured on B200 for host buffers: small first batches -- to start coding before a whole 2 GiB
+    // batch has arrived -- or small last batches -- to shorten the drain -- both LOSE a few percent: the range-coder chains of a batch
+    // take ~10 ms whatever its size, so small batches cost more compute than the fill / drain they save.)
     std::vector<u32> bfirst;
-    {
-        const u32 full = ctx->max_inflight;
-        u32 ramp[4] = {std::max(1u, full / 8), std::max(1u, full / 8), std::max(1u, full / 4), std::max(1u, full / 2)};
-        const u32 rsum = ramp[0] + ramp[1] + ramp[2] + ramp[3];
-        u32 pos = 0;
-        if (!on_device && full >= 64 && n >= 2 * rsum + full && !getenv("DSRCGPU_NO_RAMP")) {
-            for (int k = 0; k < 4; ++k) { bfirst.push_back(pos); pos += ramp[k]; }
-            while (n - pos - rsum >= full) { bfirst.push_back(pos); pos += full; }
-            if (n - pos > rsum) { bfirst.push_back(pos); pos = n - rsum; }
-            for (int k = 3; k >= 0; --k) { bfirst.push_back(pos); pos += ramp[k]; }
-        } else {
-            for (; pos < n; pos += full) bfirst.push_back(pos);
-        }
-        bfirst.push_back(n);
-    }
+    for (u32 pos = 0; pos < n; pos += ctx->max_inflight) bfirst.push_back(pos);
+    bfirst.push_back(n);
     const u32 nb = (u32)bfirst.size() - 1;
     u64 out_pos = 0;
     u32 retired = 0;
@@ -423,14 +425,22 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         if (on_device) out_pos = end;
         else {
             if (out_pos + end > out_cap) { ctx->err = "output buffer too small"; return DSRCGPU_E_CAPACITY; }
-            CK(cudaMemcpyAsync(out + out_pos, t.out.p, end, cudaMemcpyDeviceToHost, t.stream));
+            { KTimer tcopy(ctx, &t, K_D2H); CK(cudaMemcpyAsync(out + out_pos, t.out.p, end, cudaMemcpyDeviceToHost, t.stream)); }
             out_pos += end;
         }
         return DSRCGPU_OK;
     };
 
+    // batches that have finished are retired as soon as the host gets here, not when their slot is needed again: in host mode that is
+    // what starts their output copy, and it should run beside the NEXT batch's input copy (the two directions of the link), not
+    // between two input copies
+    auto retire_ready = [&](u32 enqueued) {
+        while (rc == DSRCGPU_OK && retired < enqueued && cudaEventQuery(ctx->slots[retired % S].ev_results) == cudaSuccess) rc = retire(retired++);
+    };
     for (u32 b = 0; b < nb && rc == DSRCGPU_OK; ++b) {
         Slot& sl = ctx->slots[b % S];
+        retire_ready(b);
+        if (rc) break;
         if (sl.busy) {
             while (rc == DSRCGPU_OK && retired <= sl.batch) rc = retire(retired++);
             if (rc) break;
@@ -455,6 +465,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
                 lo = std::min(lo, o); hi = std::max(hi, o + l); sum += l;
             }
             cudaError_t e = cudaSuccess;
+            KTimer tcopy(ctx, &sl, K_H2D);
             if (asc && hi - lo <= sum + (u64)cnt * 64) {
                 e = sl.in.ensure(hi - lo + 16);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(sl.in.p, fastq + lo, hi - lo, cudaMemcpyHostToDevice, sl.stream);
@@ -476,7 +487,8 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         }
         sl.busy = true;
         rc = enqueue_batch(ctx, sl, d_in, blk_len + first, blk_tagcap ? blk_tagcap + first : nullptr, cnt, d_out, batch_out_base, batch_out_cap,
-                           on_device ? (u64*)ctx->cursor.p : nullptr, (on_device && b > 0) ? ctx->slots[(b - 1) % S].ev_sizes : nullptr);
+                           on_device ? (u64*)ctx->cursor.p : nullptr, (on_device && b > 0) ? ctx->slots[(b - 1) % S].ev_sizes : nullptr,
+                           [&]() -> int { retire_ready(b); return rc; });
         if (rc) break;
         // keep S-1 batches queued behind the one the host waits for
         while (rc == DSRCGPU_OK && retired + (u32)(S - 1) <= b && S > 1 && retired < b) rc = retire(retired++);
@@ -584,7 +596,8 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
     int start_tier = 0;                                   // raised when most blocks of a batch had to retry (large-alphabet data)
     u32 dec_batch = 65536;
     if (const char* e = getenv("DSRCGPU_DEC_BATCH")) dec_batch = (u32)std::max(1, atoi(e));
-    const u32 per_batch0 = (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / tiers[0]));
+    u32 per_batch0 = (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / tiers[0]));
+    per_batch0 = (n + (n + per_batch0 - 1) / per_batch0 - 1) / ((n + per_batch0 - 1) / per_batch0);   // equal batches: the chains of a small last batch would be latency-bound
     std::vector<u32> idx, status, sizes, retry; std::vector<u64> offs, ooffs;
     u64 out_pos = 0;
     for (u32 first = 0; first < n;) {

@@ -98,6 +98,9 @@ struct ModelShared {
 };
 static_assert(offsetof(TabShared, part) >= sizeof(ModelSortShared), "PartState must survive sort_pass / group_scan on an oversize partition");
 #define MODEL_SMEM_QUALITY (offsetof(ModelShared, u) + (sizeof(TabShared) > sizeof(ModelSortShared) ? sizeof(TabShared) : sizeof(ModelSortShared)))
+// the launch without the partition engine never touches TabShared's tail (pB, pP, part): it keeps the smaller footprint, which is what
+// lets the range-coder CTAs of the other streams' batches stay resident beside four model CTAs per SM
+#define MODEL_SMEM_QUALITY_CLASSIC (offsetof(ModelShared, u) + (offsetof(TabShared, pB) > sizeof(ModelSortShared) ? offsetof(TabShared, pB) : sizeof(ModelSortShared)))
 
 
 // ---- element sources of a sort pass. An element is (ctx << 40) | (sym << 32) | index. A warp walks consecutive rows of
@@ -749,7 +752,7 @@ void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 str
 {
     model_smem_optin();
     k_model<true, true><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride);
-    k_model<true, false><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride);
+    k_model<true, false><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY_CLASSIC, s>>>(ws, stride);
 }
 void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false, false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
 cudaError_t rc_init_device() { k_rcp_lut<<<65536 / 256, 256>>>(); return cudaDeviceSynchronize(); }
