@@ -87,6 +87,12 @@ def lib():
     L.dsrcgpu_synth_fastq_host.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
     L.dsrcgpu_cut_blocks.restype = C.c_uint64
     L.dsrcgpu_cut_blocks.argtypes = [vp, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64]
+    L.dsrcgpu_cut_blocks_window.restype = C.c_uint64
+    L.dsrcgpu_cut_blocks_window.argtypes = [vp, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64, u32p]
+    L.dsrcgpu_archive_footer_span.restype = C.c_int
+    L.dsrcgpu_archive_footer_span.argtypes = [vp, u64p, u64p]
+    L.dsrcgpu_read_archive_footer.restype = C.c_int
+    L.dsrcgpu_read_archive_footer.argtypes = [vp, vp, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64, C.POINTER(Dataset), C.POINTER(Settings)]
     L.dsrcgpu_last_call_ms.restype = C.c_float
     L.dsrcgpu_last_call_ms.argtypes = [vp]
     _lib = L

@@ -726,7 +726,13 @@ static void cut_skip_eol(const u8* d, u64& p, u64 size, bool& crlf)
 }
 extern "C" uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks)
 {
-    u64 start = 0, nb = 0; bool crlf = false;
+    uint32_t state = 0;
+    return dsrcgpu_cut_blocks_window(data, size, cbuf, off, len, max_blocks, &state);
+}
+extern "C" uint64_t dsrcgpu_cut_blocks_window(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks,
+                                              uint32_t* reader_state)
+{
+    u64 start = 0, nb = 0; bool crlf = reader_state && (*reader_state & 1u);
     bool tail_only = false;     // the previous full window ended exactly at EOF: the next Read() returns 0 and the chunk is the
                                 // carry-over as it stands -- no "- 1" for the final newline, no CRLF adjustment (FastqStream.cpp:41-69)
     if (cbuf <= 8192) return 0;
@@ -750,6 +756,7 @@ extern "C" uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint6
         if (nb < max_blocks && off && len) { off[nb] = start; len[nb] = (u32)blk; }
         ++nb; start += adv;
     }
+    if (reader_state && off && len) *reader_state = crlf ? 1u : 0u;      // only the pass that stores blocks advances the reader
     return nb;
 }
 

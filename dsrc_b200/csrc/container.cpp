@@ -107,3 +107,36 @@ extern "C" int dsrcgpu_read_archive_index(const uint8_t* arc, uint64_t size, uin
     if (cs) { cs->lossy = t[2] & 1; cs->calc_crc32 = (t[2] >> 1) & 1; cs->dna_order = t[3]; cs->quality_order = t[4]; cs->tag_preserve_flags = rd64(t + 5); }
     return DSRCGPU_OK;
 }
+
+// the same for a host that streams: it has read the 40-byte header and then the footer (at the offset / size the header names), not the
+// blocks. blk_len[i] = size of block i; block i starts at 40 + sum of the sizes before it.
+extern "C" int dsrcgpu_read_archive_footer(const uint8_t* header40, const uint8_t* footer, uint64_t footer_bytes, uint64_t file_size,
+                                           uint64_t* n_blocks, uint32_t* blk_len, uint64_t max_blocks, dsrcgpu_dataset_t* ds, dsrcgpu_settings_t* cs)
+{
+    if (!header40 || !n_blocks) return DSRCGPU_E_ARG;
+    if (header40[0] != 0xAA || header40[1] != 2) return DSRCGPU_E_MALFORMED;
+    const u32 fsize = rd32(header40 + 4); const u64 foff = rd64(header40 + 8), n = rd64(header40 + 24);
+    if (foff < 40 || foff > file_size || fsize > file_size - foff || fsize < 14) return DSRCGPU_E_MALFORMED;
+    if (n == 0 || n > ((u64)fsize - 14) / 4 || n > (foff - 40) / 16 + 1) return DSRCGPU_E_MALFORMED;
+    *n_blocks = n;
+    if (!footer) return DSRCGPU_OK;                        // header only: the caller learns where the footer is (dsrcgpu_archive_footer_span)
+    if (footer_bytes < fsize || footer[0] != 0xCC) return DSRCGPU_E_MALFORMED;
+    u64 p = 40;
+    for (u64 i = 0; i < n; ++i) {
+        const u32 v = (u32)footer[1 + 4 * i] | ((u32)footer[2 + 4 * i] << 8) | ((u32)footer[3 + 4 * i] << 16) | ((u32)footer[4 + 4 * i] << 24);
+        if (v > foff - p) return DSRCGPU_E_MALFORMED;
+        if (i < max_blocks && blk_len) blk_len[i] = v;
+        p += v;
+    }
+    const u8* t = footer + 1 + 4 * n;
+    if (ds) { ds->plus_repetition = t[0] & 1; ds->color_space = (t[0] >> 1) & 1; ds->quality_offset = t[1]; }
+    if (cs) { cs->lossy = t[2] & 1; cs->calc_crc32 = (t[2] >> 1) & 1; cs->dna_order = t[3]; cs->quality_order = t[4]; cs->tag_preserve_flags = rd64(t + 5); }
+    return DSRCGPU_OK;
+}
+extern "C" int dsrcgpu_archive_footer_span(const uint8_t* header40, uint64_t* footer_offset, uint64_t* footer_bytes)
+{
+    if (!header40 || !footer_offset || !footer_bytes) return DSRCGPU_E_ARG;
+    if (header40[0] != 0xAA || header40[1] != 2) return DSRCGPU_E_MALFORMED;
+    *footer_bytes = rd32(header40 + 4); *footer_offset = rd64(header40 + 8);
+    return DSRCGPU_OK;
+}

@@ -18,14 +18,14 @@ namespace dsrc { namespace comp {
 class BlockCompressorGpu
 {
 public:
-	BlockCompressorGpu(const fq::FastqDatasetType& type_, const CompressionSettings& settings_, uint32 maxBlockBytes_ = 8u << 20)
+	BlockCompressorGpu(const fq::FastqDatasetType& type_, const CompressionSettings& settings_, uint32 maxBlockBytes_ = 8u << 20, int device_ = 0)
 		:	ctx(NULL)
 		,	tagCapacity(0)
 	{
 		dsrcgpu_dataset_t ds = { type_.qualityOffset, (uint8_t)type_.plusRepetition, (uint8_t)type_.colorSpace };
 		dsrcgpu_settings_t cs = { settings_.dnaOrder, settings_.qualityOrder, settings_.tagPreserveFlags,
 								  (uint8_t)settings_.lossy, (uint8_t)settings_.calculateCrc32 };
-		if (dsrcgpu_create(&ctx, 0, &ds, &cs, maxBlockBytes_, 1) != DSRCGPU_OK)
+		if (dsrcgpu_create(&ctx, device_, &ds, &cs, maxBlockBytes_, 1) != DSRCGPU_OK)
 			throw DsrcException("dsrc_b200: no CUDA device or unsupported settings");
 	}
 
@@ -48,7 +48,13 @@ public:
 		tagCapacity = dsrcgpu_tag_capacity_after(tagCapacity, dsrcgpu_tag_field_count(p, titleLen));
 		if (out.size() < (size_t)len + len / 2 + 4096)
 			out.resize((size_t)len + len / 2 + 4096);
-		int rc = dsrcgpu_encode_blocks(ctx, p, &off, &len, &cap, 1, out.data(), out.size(), &size, raw, cmp);
+		int rc = DSRCGPU_E_CAPACITY;
+		for (int attempt = 0; attempt < 4 && rc == DSRCGPU_E_CAPACITY; ++attempt)		// a tiny block with many text fields can exceed 1.5x its input
+		{
+			if (attempt > 0)
+				out.resize(out.size() * 4);
+			rc = dsrcgpu_encode_blocks(ctx, p, &off, &len, &cap, 1, out.data(), out.size(), &size, raw, cmp);
+		}
 		if (rc != DSRCGPU_OK)
 			throw DsrcException(dsrcgpu_last_error(ctx));
 		for (int i = 0; i < 4; ++i)

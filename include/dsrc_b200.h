@@ -102,6 +102,13 @@ uint32_t dsrcgpu_tag_capacity_after(uint32_t capacity_before, uint32_t n_fields)
  * (CLI: -b MB << 20). Pure host function. Returns the number of blocks (only the first max_blocks are stored). */
 uint64_t dsrcgpu_cut_blocks(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks);
 
+/* The same for a host that STREAMS the file through a bounded window (the reference's reader keeps one chunk buffer, src/FastqStream.h:74-89):
+ * data[0..size) is a window of the file that starts at a block boundary; reader_state carries the one piece of reader state that outlives
+ * a chunk (usesCrlf) from window to window -- 0 before the first one. The last block of a window that is not the end of the file was cut
+ * at the window's end, not at a record: drop it and start the next window at its offset. */
+uint64_t dsrcgpu_cut_blocks_window(const uint8_t* data, uint64_t size, uint64_t cbuf, uint64_t* off, uint32_t* len, uint64_t max_blocks,
+                                   uint32_t* reader_state);
+
 /* == FastqParser::Analyze (src/FastqParser.cpp:27-138) on the first chunk: fills plus_repetition / color_space and, when
  * ds->quality_offset is 0 on entry, the auto-detected quality offset. DSRCGPU_E_MALFORMED == "Error analyzing FASTQ dataset". Pure host. */
 int dsrcgpu_analyze_first_chunk(const uint8_t* chunk, uint64_t size, dsrcgpu_dataset_t* ds);
@@ -114,6 +121,12 @@ int dsrcgpu_write_archive_footer(uint8_t* out, uint64_t out_cap, const uint32_t*
                                  const dsrcgpu_dataset_t* ds, const dsrcgpu_settings_t* cs);
 int dsrcgpu_read_archive_index(const uint8_t* arc, uint64_t size, uint64_t* n_blocks, uint64_t* blk_off, uint32_t* blk_len,
                                uint64_t max_blocks, dsrcgpu_dataset_t* ds, dsrcgpu_settings_t* cs);
+
+/* header / footer for a host that streams the archive: footer position from the 40-byte header, then the index from the footer alone
+ * (block i starts at 40 + the sizes before it). footer == NULL: validate the header and return the block count only. */
+int dsrcgpu_archive_footer_span(const uint8_t* header40, uint64_t* footer_offset, uint64_t* footer_bytes);
+int dsrcgpu_read_archive_footer(const uint8_t* header40, const uint8_t* footer, uint64_t footer_bytes, uint64_t file_size,
+                                uint64_t* n_blocks, uint32_t* blk_len, uint64_t max_blocks, dsrcgpu_dataset_t* ds, dsrcgpu_settings_t* cs);
 
 /* device-timed duration (ms, CUDA events on the context's stream) of the last encode/decode call */
 float dsrcgpu_last_call_ms(dsrcgpu_ctx* ctx);

@@ -92,3 +92,25 @@ def test_module_compress_decompress(tmp_path):
     assert open(arc, "rb").read() == open(a_ref, "rb").read()
     rc, err = gpu.module_roundtrip(str(tmp_path / "missing"), arc, back, 2, 2, 1)
     assert rc != 0 and "Cannot open file to read:" in err
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_operator_streams_the_file_through_a_bounded_window(tmp_path, monkeypatch, crlf):
+    """host/DsrcOperatorGpu.h is windowed (bounded host RAM whatever the file size): with a 4 MiB window a 13 MB file goes through in
+    four windows of 1 MB chunks -- the blocks at the window seams, the carried field-vector capacity and the reader's
+    CRLF state must come out exactly as `dsrc c -t1` writes them; the decompressor is windowed too."""
+    import synth
+    monkeypatch.setenv("DSRCGPU_WINDOW_MB", "4")
+    big = synth.illumina(30000, seed=61, small_field=True, crlf=crlf) + synth.exact_size(3 << 20, seed=62, crlf=crlf)
+    assert len(big) > (12 << 20)
+    src, a_ref, a_gpu, back = (str(tmp_path / n) for n in ("in.fastq", "ref.dsrc", "gpu.dsrc", "gpu.fastq"))
+    open(src, "wb").write(big)
+    assert refbind.Ref().compress_file(src, a_ref, 2, 2, 1, threads=1) == 0
+    gpu = refbind.Shim()
+    rc, err = gpu.compress_file(src, a_gpu, 2, 2, 1)
+    assert rc == 0, err
+    assert open(a_gpu, "rb").read() == open(a_ref, "rb").read()
+    monkeypatch.setenv("DSRCGPU_WINDOW_MB", "2")          # 512 KiB of compressed blocks per window on the way back
+    rc, err = gpu.decompress_file(a_ref, back)
+    assert rc == 0, err
+    assert open(back, "rb").read() == big.replace(b"\r\n", b"\n")

@@ -204,3 +204,33 @@ def test_product_cutter_matches_oracle_including_exact_window_eof():
         for cb in (cbuf, 1 << 18, 100000):
             off, ln = cut_blocks(data, cb)
             assert [(int(a), int(b)) for a, b in zip(off, ln)] == [(int(a), int(b)) for a, b in o.cut(data, cb)], (len(data), cb)
+
+
+def test_windowed_cutter_matches_whole_file_cutter():
+    """dsrcgpu_cut_blocks_window (what the streaming C++ operator uses, host/DsrcOperatorGpu.h): cutting a file window by window -- dropping
+    every window's last block and restarting there, carrying the reader's CRLF state -- gives the whole-file block queue"""
+    import ctypes as C
+    from dsrc_b200 import _lib
+    L = _lib.lib()
+    for crlf in (False, True):
+        big = synth.illumina(12000, seed=61, small_field=True, crlf=crlf) + synth.exact_size(3 << 20, seed=62, crlf=crlf)
+        buf = np.frombuffer(big, dtype=np.uint8)
+        cb = 1 << 20
+        whole = [(int(a), int(b)) for a, b in refbind.Oracle().cut(big, cb)]
+        for win in (4 << 20, 5 << 20, (3 << 20) + 12345):
+            pos, got = 0, []
+            st = np.zeros(1, dtype=np.uint32)
+            while pos < len(big):
+                w = min(win, len(big) - pos)
+                last = pos + w == len(big)
+                sub = buf[pos:pos + w]
+                st2 = st.copy()
+                k = L.dsrcgpu_cut_blocks_window(sub.ctypes.data_as(C.c_void_p), w, cb, None, None, 0, st2.ctypes.data_as(_lib.u32p))
+                o = np.zeros(k, dtype=np.uint64)
+                ln = np.zeros(k, dtype=np.uint32)
+                L.dsrcgpu_cut_blocks_window(sub.ctypes.data_as(C.c_void_p), w, cb, o.ctypes.data_as(_lib.u64p), ln.ctypes.data_as(_lib.u32p), k, st.ctypes.data_as(_lib.u32p))
+                take = k if last else k - 1
+                assert take > 0
+                got += [(int(a) + pos, int(b)) for a, b in zip(o[:take], ln[:take])]
+                pos = len(big) if last else pos + int(o[take])
+            assert got == whole, (crlf, win)
