@@ -43,6 +43,8 @@ static const char* K_NAMES[K_NUM] = {"count_lines", "parse", "preprocess", "tags
 // that the copies of one batch, the parallel kernels of the next and the serial range-coder chains of a third overlap.
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_r = nullptr;                         // serial stage of the batch (range-coder chains, sizes, gather, output copy): high priority
+    cudaEvent_t ev_pdone = nullptr;                          // the batch's parallel stage (everything up to the model kernels) has finished
     DevBuf in, desc, state, result, probe, lines, qcat, dcat, trip_q, trip_d, ftab, streams, out;
     DevBuf r_title_off, r_seq_off, r_qua_off, r_title_len, r_qua_len, r_dna_len, r_trunc_len, r_qcat_off, r_dcat_off;
     DevBuf elem_a, elem_b, tagpool, q0_arena, queue;        // per-CTA arenas of the persistent kernels, block queue counters
@@ -64,8 +66,10 @@ struct Slot {
         if (ev_results) cudaEventDestroy(ev_results);
         if (ev_sizes) cudaEventDestroy(ev_sizes);
         if (ev_probe) cudaEventDestroy(ev_probe);
+        if (ev_pdone) cudaEventDestroy(ev_pdone);
         if (stream) cudaStreamDestroy(stream);
-        ev_results = ev_sizes = ev_probe = nullptr; stream = nullptr;
+        if (stream_r) cudaStreamDestroy(stream_r);
+        ev_results = ev_sizes = ev_probe = ev_pdone = nullptr; stream = nullptr; stream_r = nullptr;
     }
 };
 
@@ -85,7 +89,9 @@ struct dsrcgpu_ctx {
     float k_ms[K_NUM]; u32 k_launches[K_NUM];
     cudaEvent_t call_a = nullptr, call_b = nullptr; float call_ms = 0;
     bool profiling = true, phase_prof = false;
+    int p_serial = 2;                                // where a batch waits for the previous batch's parallel stage: 0 nowhere, 1 before parse, 2 before the model kernels
 };
+static inline cudaStream_t rstream(const Slot& sl) { return sl.stream_r ? sl.stream_r : sl.stream; }
 
 static cudaEvent_t get_event(dsrcgpu_ctx* ctx)
 {
@@ -93,13 +99,13 @@ static cudaEvent_t get_event(dsrcgpu_ctx* ctx)
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct KTimer {
-    dsrcgpu_ctx* ctx; Slot* sl; int k; cudaEvent_t a = nullptr, b = nullptr;
-    KTimer(dsrcgpu_ctx* c, Slot* s, int kid) : ctx(c), sl(s), k(kid)
+    dsrcgpu_ctx* ctx; Slot* sl; int k; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    KTimer(dsrcgpu_ctx* c, Slot* s, int kid, cudaStream_t on = nullptr) : ctx(c), sl(s), k(kid), st(on ? on : s->stream)
     {
         ctx->k_launches[k]++;
-        if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, sl->stream); }
+        if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, st); }
     }
-    ~KTimer() { if (ctx->profiling) { cudaEventRecord(b, sl->stream); sl->ev_used.push_back({k, {a, b}}); } }
+    ~KTimer() { if (ctx->profiling) { cudaEventRecord(b, st); sl->ev_used.push_back({k, {a, b}}); } }
 };
 static void collect_times(dsrcgpu_ctx* ctx, Slot* sl)
 {
@@ -146,9 +152,19 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     int ns = 3;
     if (const char* e = getenv("DSRCGPU_SLOTS")) ns = atoi(e);
     ctx->n_slots = std::max(1, std::min(ns, (int)MAX_SLOTS));
+    if (const char* e = getenv("DSRCGPU_PSERIAL")) ctx->p_serial = atoi(e);
+    // The model launches of successive batches run one after another (DSRCGPU_PSERIAL=2: two model launches side by side only stretch
+    // each other), the serial stage of a batch -- latency-bound range-coder chains at ~5 % occupancy -- runs beside the next batch's
+    // parallel stage. DSRCGPU_RSTREAM=1 moves the serial stage to a high-priority stream of its own (developer switch).
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool rstream_on = false;                         // measured on B200: no gain over the slot's own stream (the chains are placed early enough either way)
+    if (const char* e = getenv("DSRCGPU_RSTREAM")) rstream_on = atoi(e) != 0;
     for (int i = 0; i < ctx->n_slots; ++i) {
         Slot& sl = ctx->slots[i];
         if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            (rstream_on && cudaStreamCreateWithPriority(&sl.stream_r, cudaStreamNonBlocking, prio_hi) != cudaSuccess) ||
+            cudaEventCreateWithFlags(&sl.ev_pdone, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&sl.ev_results, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&sl.ev_sizes, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&sl.ev_probe, cudaEventDisableTiming) != cudaSuccess) {
@@ -182,7 +198,7 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (int i = 0; i < ctx->n_slots; ++i) { if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream); ctx->slots[i].release(); }
+    for (int i = 0; i < ctx->n_slots; ++i) { if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream); if (ctx->slots[i].stream_r) cudaStreamSynchronize(ctx->slots[i].stream_r); ctx->slots[i].release(); }
     ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release(); ctx->tab.release(); ctx->tab_mask.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->call_a) cudaEventDestroy(ctx->call_a);
@@ -250,7 +266,7 @@ static int status_to_error(dsrcgpu_ctx* ctx, u32 status, u32 blk)
 // `idle` is called over and over while the host waits for the layout probe (i.e. for this batch's input copy): the scheduler uses it
 // to retire batches that finish meanwhile, so that their output copies start at once and run beside this input copy.
 static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* blk_len, const u32* blk_tagcap, u32 n,
-                         u8* d_out, u64 out_base, u64 out_cap, u64* cursor, cudaEvent_t wait_sizes, const std::function<int()>& idle)
+                         u8* d_out, u64 out_base, u64 out_cap, u64* cursor, cudaEvent_t wait_sizes, cudaEvent_t wait_p, const std::function<int()>& idle)
 {
     int rc = ensure_host(ctx, sl, n);
     if (rc) return rc;
@@ -343,21 +359,26 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     ws.tagpool = (u8*)sl.tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
 
     CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    if (wait_p && ctx->p_serial == 1) CK(cudaStreamWaitEvent(s, wait_p, 0));
     { KTimer t(ctx, &sl, K_PARSE); launch_parse(ws, s); }
     if (ws.calc_crc) { KTimer t(ctx, &sl, K_CRC); launch_crc(ws, s, 0); }
     { KTimer t(ctx, &sl, K_PREP); launch_preprocess(ws, s); }
     { KTimer t(ctx, &sl, K_TAGS); launch_tags(ws, s, ctx->tag_ctas); }
+    if (wait_p && ctx->p_serial == 2) CK(cudaStreamWaitEvent(s, wait_p, 0));
     if (rc_q) { KTimer t(ctx, &sl, K_MODEL_Q); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
     else { KTimer t(ctx, &sl, K_Q0); launch_q0_quality(ws, s, (u8*)sl.q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
     if (rc_d) { KTimer t(ctx, &sl, K_MODEL_D); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
     else { KTimer t(ctx, &sl, K_D0); launch_d0_dna(ws, s, (u8*)sl.q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
-    if (rc_q || rc_d) { KTimer t(ctx, &sl, K_RC); launch_rc_encode(ws, s); }
-    if (wait_sizes) CK(cudaStreamWaitEvent(s, wait_sizes, 0));       // the previous batch has to publish where its output ends
-    { KTimer t(ctx, &sl, K_SIZES); launch_meta_and_sizes(ws, s, out_base, cursor); }
-    CK(cudaEventRecord(sl.ev_sizes, s));
-    { KTimer t(ctx, &sl, K_GATHER); launch_gather(ws, s); }
-    CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(sl.ev_results, s));
+    CK(cudaEventRecord(sl.ev_pdone, s));
+    const cudaStream_t r = rstream(sl);
+    if (r != s) CK(cudaStreamWaitEvent(r, sl.ev_pdone, 0));
+    if (rc_q || rc_d) { KTimer t(ctx, &sl, K_RC, r); launch_rc_encode(ws, r); }
+    if (wait_sizes) CK(cudaStreamWaitEvent(r, wait_sizes, 0));       // the previous batch has to publish where its output ends
+    { KTimer t(ctx, &sl, K_SIZES, r); launch_meta_and_sizes(ws, r, out_base, cursor); }
+    CK(cudaEventRecord(sl.ev_sizes, r));
+    { KTimer t(ctx, &sl, K_GATHER, r); launch_gather(ws, r); }
+    CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, r));
+    CK(cudaEventRecord(sl.ev_results, r));
     CK(cudaGetLastError());
     sl.ws = ws;
     return DSRCGPU_OK;
@@ -365,7 +386,7 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
 
 static void abort_all(dsrcgpu_ctx* ctx)
 {
-    for (int i = 0; i < ctx->n_slots; ++i) { cudaStreamSynchronize(ctx->slots[i].stream); collect_times(ctx, &ctx->slots[i]); ctx->slots[i].busy = false; }
+    for (int i = 0; i < ctx->n_slots; ++i) { cudaStreamSynchronize(ctx->slots[i].stream); cudaStreamSynchronize(rstream(ctx->slots[i])); collect_times(ctx, &ctx->slots[i]); ctx->slots[i].busy = false; }
 }
 
 // The CUDA-stream block scheduler (replaces the worker pool + queues of DsrcCompressorMT, src/DsrcOperator.cpp:230-394):
@@ -408,10 +429,10 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
             if (grow) {
                 CK(t.out.ensure(need + 64));
                 t.ws.out = (u8*)t.out.p; t.ws.out_cap = need + 64;
-                launch_meta_and_sizes(t.ws, t.stream, 0, nullptr);
-                launch_gather(t.ws, t.stream);
-                CK(cudaMemcpyAsync(t.h_result, t.result.p, sizeof(BlockResult) * t.cnt, cudaMemcpyDeviceToHost, t.stream));
-                CK(cudaStreamSynchronize(t.stream));
+                launch_meta_and_sizes(t.ws, rstream(t), 0, nullptr);
+                launch_gather(t.ws, rstream(t));
+                CK(cudaMemcpyAsync(t.h_result, t.result.p, sizeof(BlockResult) * t.cnt, cudaMemcpyDeviceToHost, rstream(t)));
+                CK(cudaStreamSynchronize(rstream(t)));
             }
         }
         for (u32 i = 0; i < t.cnt; ++i) {
@@ -425,7 +446,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         if (on_device) out_pos = end;
         else {
             if (out_pos + end > out_cap) { ctx->err = "output buffer too small"; return DSRCGPU_E_CAPACITY; }
-            { KTimer tcopy(ctx, &t, K_D2H); CK(cudaMemcpyAsync(out + out_pos, t.out.p, end, cudaMemcpyDeviceToHost, t.stream)); }
+            { KTimer tcopy(ctx, &t, K_D2H, rstream(t)); CK(cudaMemcpyAsync(out + out_pos, t.out.p, end, cudaMemcpyDeviceToHost, rstream(t))); }
             out_pos += end;
         }
         return DSRCGPU_OK;
@@ -444,7 +465,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         if (sl.busy) {
             while (rc == DSRCGPU_OK && retired <= sl.batch) rc = retire(retired++);
             if (rc) break;
-            cudaError_t e = cudaStreamSynchronize(sl.stream);            // its output copy has left the staging buffer
+            cudaError_t e = cudaStreamSynchronize(rstream(sl));           // its output copy has left the staging buffer
             if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = DSRCGPU_E_CUDA; break; }
             sl.busy = false;
         }
@@ -488,6 +509,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         sl.busy = true;
         rc = enqueue_batch(ctx, sl, d_in, blk_len + first, blk_tagcap ? blk_tagcap + first : nullptr, cnt, d_out, batch_out_base, batch_out_cap,
                            on_device ? (u64*)ctx->cursor.p : nullptr, (on_device && b > 0) ? ctx->slots[(b - 1) % S].ev_sizes : nullptr,
+                           (b > 0 && S > 1) ? ctx->slots[(b - 1) % S].ev_pdone : nullptr,
                            [&]() -> int { retire_ready(b); return rc; });
         if (rc) break;
         // keep S-1 batches queued behind the one the host waits for
@@ -496,13 +518,16 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     while (rc == DSRCGPU_OK && retired < nb) rc = retire(retired++);
     if (rc) { abort_all(ctx); return rc; }
     // join every stream into slot 0's for the call timing, then wait
-    for (int i = 1; i < S; ++i) {
-        cudaEvent_t e = get_event(ctx);
-        cudaEventRecord(e, ctx->slots[i].stream); cudaStreamWaitEvent(ctx->slots[0].stream, e, 0);
-        ctx->ev_pool.push_back(e);
+    for (int i = 0; i < S; ++i) {
+        for (cudaStream_t st : {ctx->slots[i].stream, ctx->slots[i].stream_r}) {
+            if (!st || st == ctx->slots[0].stream) continue;
+            cudaEvent_t e = get_event(ctx);
+            cudaEventRecord(e, st); cudaStreamWaitEvent(ctx->slots[0].stream, e, 0);
+            ctx->ev_pool.push_back(e);
+        }
     }
     cudaEventRecord(ctx->call_b, ctx->slots[0].stream);
-    for (int i = 0; i < S; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].stream)); ctx->slots[i].busy = false; }
+    for (int i = 0; i < S; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].stream)); CK(cudaStreamSynchronize(rstream(ctx->slots[i]))); ctx->slots[i].busy = false; }
     CK(cudaEventSynchronize(ctx->call_b));
     cudaEventElapsedTime(&ctx->call_ms, ctx->call_a, ctx->call_b);
     return DSRCGPU_OK;

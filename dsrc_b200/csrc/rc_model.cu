@@ -444,6 +444,7 @@ __device__ void group_scan(ModelShared& S, const u64* sorted, u32* longq, u64* t
 }
 
 #include "model_part.cuh"
+#include "model_walk.cuh"
 
 // Pool of adaptive-row tables shared by every model CTA of the context (all slots): bit set = table in use. A table is
 // all-zero whenever it is in the pool. The pool holds one table per CTA that can be resident (4 per SM), so a CTA never
@@ -498,7 +499,7 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
         // ---- scheme selection. Only thread 0 looks at (and may set) the block's status; everybody else learns the outcome from
         // shared memory after the barrier, so the whole CTA takes the same path through next_block()'s barriers
         if (tid == 0) {
-            S.ok = st.status == ST_OK;
+            S.ok = st.status == ST_OK && !(QUALITY && st.pad[1]);      // pad[1]: the walk engine's launch (model_walk.cuh) has coded the block
             S.M = 0;
             if (!S.ok) {}
             else if (QUALITY) {
@@ -619,6 +620,16 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 // and, for quality, the 256-bit symbol mask of TTranslationalQualityEncoder::Store (QualityEncoder.h:332-342).
 // ------------------------------------------------------------------------------------------------
 #define RC_CTA 64
+#ifndef RC_L2HINT
+#define RC_L2HINT 0
+#endif
+#if RC_L2HINT == 128
+#define RC_L2 ".L2::128B"
+#elif RC_L2HINT == 256
+#define RC_L2 ".L2::256B"
+#else
+#define RC_L2 ""
+#endif
 #ifndef RC_RING
 #define RC_RING 6
 #endif
@@ -698,8 +709,8 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(Workspace ws, u32 do_q
     // group counting of wait_group is uniform
 #define RC_FETCH(g, so) do { \
         if ((g) < G) { \
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rb + (so)), "l"(trip + 2 * (g)) : "memory"); \
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rb + (so) + HALF), "l"(trip + 2 * (g) + 1) : "memory"); \
+            asm volatile("cp.async.cg.shared.global" RC_L2 " [%0], [%1], 16;" :: "r"(rb + (so)), "l"(trip + 2 * (g)) : "memory"); \
+            asm volatile("cp.async.cg.shared.global" RC_L2 " [%0], [%1], 16;" :: "r"(rb + (so) + HALF), "l"(trip + 2 * (g) + 1) : "memory"); \
         } \
         asm volatile("cp.async.commit_group;" ::: "memory"); } while (0)
 #pragma unroll
@@ -751,6 +762,11 @@ static void model_smem_optin()
 void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride)
 {
     model_smem_optin();
+    {   // blocks with <= 5 quality values and one read length: tables in shared memory, one warp per position bucket (model_walk.cuh)
+        cudaFuncSetAttribute(k_model_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkShared));
+        const u32 g = ws.n_blocks < 148u * 2u ? ws.n_blocks : 148u * 2u;
+        k_model_walk<<<g ? g : 1, WALK_CTA, sizeof(WalkShared), s>>>(ws);
+    }
     k_model<true, true><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride);
     k_model<true, false><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY_CLASSIC, s>>>(ws, stride);
 }
