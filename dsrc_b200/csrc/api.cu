@@ -51,6 +51,8 @@ struct Slot {
     BlockDesc* h_desc = nullptr; BlockResult* h_result = nullptr; BlockProbe* h_probe = nullptr; u32 h_cap = 0;
     cudaEvent_t ev_results = nullptr, ev_sizes = nullptr, ev_probe = nullptr;
     bool busy = false; u32 first = 0, cnt = 0, batch = 0;
+    bool r_enq = false;                                      // the batch's serial stage (chains, sizes, gather, result copy) has been enqueued
+    u64 r_out_base = 0; u64* r_cursor = nullptr;             // arguments of the size scan, kept until then
     Workspace ws{};                                          // of the batch in flight (re-used if its output staging has to grow)
     std::vector<u64> offs;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_used;
@@ -89,6 +91,7 @@ struct dsrcgpu_ctx {
     float k_ms[K_NUM]; u32 k_launches[K_NUM];
     cudaEvent_t call_a = nullptr, call_b = nullptr; float call_ms = 0;
     bool profiling = true, phase_prof = false;
+    int rc_group = 2;                                // batches whose range-coder chains share one launch (<= n_slots, RC_GROUP_MAX)
     int p_serial = 2;                                // where a batch waits for the previous batch's parallel stage: 0 nowhere, 1 before parse, 2 before the model kernels
 };
 static inline cudaStream_t rstream(const Slot& sl) { return sl.stream_r ? sl.stream_r : sl.stream; }
@@ -153,6 +156,8 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     if (const char* e = getenv("DSRCGPU_SLOTS")) ns = atoi(e);
     ctx->n_slots = std::max(1, std::min(ns, (int)MAX_SLOTS));
     if (const char* e = getenv("DSRCGPU_PSERIAL")) ctx->p_serial = atoi(e);
+    if (const char* e = getenv("DSRCGPU_RC_GROUP")) ctx->rc_group = atoi(e);
+    ctx->rc_group = std::max(1, std::min(ctx->rc_group, std::min((int)RC_GROUP_MAX, std::max(1, ctx->n_slots - 1))));
     // The model launches of successive batches run one after another (DSRCGPU_PSERIAL=2: two model launches side by side only stretch
     // each other), the serial stage of a batch -- latency-bound range-coder chains at ~5 % occupancy -- runs beside the next batch's
     // parallel stage. DSRCGPU_RSTREAM=1 moves the serial stage to a high-priority stream of its own (developer switch).
@@ -266,7 +271,7 @@ static int status_to_error(dsrcgpu_ctx* ctx, u32 status, u32 blk)
 // `idle` is called over and over while the host waits for the layout probe (i.e. for this batch's input copy): the scheduler uses it
 // to retire batches that finish meanwhile, so that their output copies start at once and run beside this input copy.
 static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* blk_len, const u32* blk_tagcap, u32 n,
-                         u8* d_out, u64 out_base, u64 out_cap, u64* cursor, cudaEvent_t wait_sizes, cudaEvent_t wait_p, const std::function<int()>& idle)
+                         u8* d_out, u64 out_base, u64 out_cap, u64* cursor, cudaEvent_t wait_p, const std::function<int()>& idle)
 {
     int rc = ensure_host(ctx, sl, n);
     if (rc) return rc;
@@ -370,17 +375,43 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     if (rc_d) { KTimer t(ctx, &sl, K_MODEL_D); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
     else { KTimer t(ctx, &sl, K_D0); launch_d0_dna(ws, s, (u8*)sl.q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
     CK(cudaEventRecord(sl.ev_pdone, s));
-    const cudaStream_t r = rstream(sl);
-    if (r != s) CK(cudaStreamWaitEvent(r, sl.ev_pdone, 0));
-    if (rc_q || rc_d) { KTimer t(ctx, &sl, K_RC, r); launch_rc_encode(ws, r); }
-    if (wait_sizes) CK(cudaStreamWaitEvent(r, wait_sizes, 0));       // the previous batch has to publish where its output ends
-    { KTimer t(ctx, &sl, K_SIZES, r); launch_meta_and_sizes(ws, r, out_base, cursor); }
-    CK(cudaEventRecord(sl.ev_sizes, r));
-    { KTimer t(ctx, &sl, K_GATHER, r); launch_gather(ws, r); }
-    CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * n, cudaMemcpyDeviceToHost, r));
-    CK(cudaEventRecord(sl.ev_results, r));
     CK(cudaGetLastError());
-    sl.ws = ws;
+    sl.ws = ws; sl.r_enq = false; sl.r_out_base = out_base; sl.r_cursor = cursor;
+    return DSRCGPU_OK;
+}
+
+// Serial stage of a group of batches (consecutive batches, in order): ONE launch of the range-coder chains for all of them -- the
+// launch is latency-bound, its duration does not depend on the number of chains at these sizes -- then per batch the size scan
+// (chained through the device cursor for device-resident output), the gather and the result read-back.
+static int finish_group(dsrcgpu_ctx* ctx, Slot** members, u32 n, cudaEvent_t wait_sizes)
+{
+    if (!n) return DSRCGPU_OK;
+    const bool rc_q = ctx->cs.quality_order > 0, rc_d = ctx->cs.dna_order > 0;
+    Slot& last = *members[n - 1];
+    const cudaStream_t r = rstream(last);
+    if (rc_q || rc_d) {
+        RcGroup grp{}; grp.n = n;
+        for (u32 k = 0; k < n; ++k) { grp.ws[k] = members[k]->ws; if (members[k] != &last || r != last.stream) CK(cudaStreamWaitEvent(r, members[k]->ev_pdone, 0)); }
+        { KTimer t(ctx, &last, K_RC, r); launch_rc_encode(grp, r); }
+    }
+    cudaEvent_t ev_rc = get_event(ctx);
+    CK(cudaEventRecord(ev_rc, r));
+    for (u32 k = 0; k < n; ++k) {
+        Slot& sl = *members[k];
+        const cudaStream_t rs = rstream(sl);
+        if (rs != r) CK(cudaStreamWaitEvent(rs, ev_rc, 0));
+        if (rs != sl.stream) CK(cudaStreamWaitEvent(rs, sl.ev_pdone, 0));
+        if (wait_sizes) CK(cudaStreamWaitEvent(rs, wait_sizes, 0));       // the previous batch has to publish where its output ends
+        { KTimer t(ctx, &sl, K_SIZES, rs); launch_meta_and_sizes(sl.ws, rs, sl.r_out_base, sl.r_cursor); }
+        CK(cudaEventRecord(sl.ev_sizes, rs));
+        { KTimer t(ctx, &sl, K_GATHER, rs); launch_gather(sl.ws, rs); }
+        CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * sl.cnt, cudaMemcpyDeviceToHost, rs));
+        CK(cudaEventRecord(sl.ev_results, rs));
+        sl.r_enq = true;
+        wait_sizes = sl.r_cursor ? sl.ev_sizes : nullptr;
+    }
+    ctx->ev_pool.push_back(ev_rc);
+    CK(cudaGetLastError());
     return DSRCGPU_OK;
 }
 
@@ -416,8 +447,19 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     u32 retired = 0;
     int rc = DSRCGPU_OK;
 
+    // batches whose parallel stage is enqueued and whose serial stage waits for the group to fill
+    Slot* group[RC_GROUP_MAX]; u32 n_group = 0;
+    cudaEvent_t prev_sizes = nullptr;
+    auto close_group = [&]() -> int {
+        const int r = finish_group(ctx, group, n_group, prev_sizes);
+        if (n_group && on_device) prev_sizes = group[n_group - 1]->ev_sizes;
+        n_group = 0;
+        return r;
+    };
+
     auto retire = [&](u32 r) -> int {
         Slot& t = ctx->slots[r % S];
+        if (!t.r_enq) { const int g = close_group(); if (g) return g; }      // (the schedule closes groups before their batches are due)
         CK(cudaEventSynchronize(t.ev_results));
         collect_times(ctx, &t);
         u64 end = on_device ? out_pos : 0;
@@ -456,7 +498,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     // what starts their output copy, and it should run beside the NEXT batch's input copy (the two directions of the link), not
     // between two input copies
     auto retire_ready = [&](u32 enqueued) {
-        while (rc == DSRCGPU_OK && retired < enqueued && cudaEventQuery(ctx->slots[retired % S].ev_results) == cudaSuccess) rc = retire(retired++);
+        while (rc == DSRCGPU_OK && retired < enqueued && ctx->slots[retired % S].r_enq && cudaEventQuery(ctx->slots[retired % S].ev_results) == cudaSuccess) rc = retire(retired++);
     };
     for (u32 b = 0; b < nb && rc == DSRCGPU_OK; ++b) {
         Slot& sl = ctx->slots[b % S];
@@ -508,10 +550,12 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         }
         sl.busy = true;
         rc = enqueue_batch(ctx, sl, d_in, blk_len + first, blk_tagcap ? blk_tagcap + first : nullptr, cnt, d_out, batch_out_base, batch_out_cap,
-                           on_device ? (u64*)ctx->cursor.p : nullptr, (on_device && b > 0) ? ctx->slots[(b - 1) % S].ev_sizes : nullptr,
+                           on_device ? (u64*)ctx->cursor.p : nullptr,
                            (b > 0 && S > 1) ? ctx->slots[(b - 1) % S].ev_pdone : nullptr,
                            [&]() -> int { retire_ready(b); return rc; });
         if (rc) break;
+        group[n_group++] = &sl;
+        if ((int)n_group >= ctx->rc_group || b + 1 == nb) { rc = close_group(); if (rc) break; }
         // keep S-1 batches queued behind the one the host waits for
         while (rc == DSRCGPU_OK && retired + (u32)(S - 1) <= b && S > 1 && retired < b) rc = retire(retired++);
     }

@@ -9,7 +9,9 @@ void launch_tags(const Workspace& ws, cudaStream_t s, u32 ctas);   // ctas = num
 // order-k contexts -> (freq,cum,tot) triples; ctas = persistent CTAs owning a sort arena of `stride` entries each
 void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
 void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride);
-void launch_rc_encode(const Workspace& ws, cudaStream_t s);       // serial range-coder chains, one thread per (block, stream)
+#define RC_GROUP_MAX 4
+struct RcGroup { Workspace ws[RC_GROUP_MAX]; u32 n; };            // the batches (slots) whose chains one launch codes
+void launch_rc_encode(const RcGroup& grp, cudaStream_t s);        // serial range-coder chains, one thread per (block, stream)
 cudaError_t rc_init_device();                                      // fills the reciprocal table of the chains on the current device (once per context)
 // -q0: positional / truncated / RLE Huffman; -d0: 2-bit pack / Huffman. arena: ctas x stride bytes of per-CTA scratch
 void launch_q0_quality(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u32 ctas);

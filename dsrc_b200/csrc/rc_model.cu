@@ -635,9 +635,15 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 #endif
 __device__ u32 g_rcp_lut[65536];                     // floor((2^32-1) / tot), filled once per device by k_rcp_lut
 __global__ void k_rcp_lut() { const u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t < 65536) g_rcp_lut[t] = t ? 0xFFFFFFFFu / t : 0u; }
-__global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(Workspace ws, u32 do_quality, u32 do_dna)
+// A launch codes the chains of up to RC_GROUP_MAX batches (slots) at once: the launch is latency-bound -- ~107 K dependent steps
+// per chain, under one resident warp per scheduler for one 8192-block batch -- so it takes the same time for two batches as for one.
+__global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_quality, u32 do_dna)
 {
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 per = do_quality + do_dna;
+    u32 g = 0;
+    while (g + 1 < grp.n && t >= grp.ws[g].n_blocks * per) { t -= grp.ws[g].n_blocks * per; ++g; }
+    const Workspace& ws = grp.ws[g];
     const u32 n = ws.n_blocks;
     u32 blk, is_dna;
     if (do_quality && do_dna) { is_dna = t >= n; blk = is_dna ? t - n : t; }
@@ -772,10 +778,11 @@ void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 str
 }
 void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false, false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
 cudaError_t rc_init_device() { k_rcp_lut<<<65536 / 256, 256>>>(); return cudaDeviceSynchronize(); }
-void launch_rc_encode(const Workspace& ws, cudaStream_t s)
+void launch_rc_encode(const RcGroup& grp, cudaStream_t s)
 {
-    const u32 dq = ws.qua_order > 0, dd = ws.dna_order > 0;
-    if (!dq && !dd) return;
-    const u32 threads = ws.n_blocks * (dq + dd);
-    k_rc_encode<<<(threads + RC_CTA - 1) / RC_CTA, RC_CTA, 0, s>>>(ws, dq, dd);
+    const u32 dq = grp.ws[0].qua_order > 0, dd = grp.ws[0].dna_order > 0;
+    if (!grp.n || (!dq && !dd)) return;
+    u32 threads = 0;
+    for (u32 g = 0; g < grp.n; ++g) threads += grp.ws[g].n_blocks * (dq + dd);
+    k_rc_encode<<<(threads + RC_CTA - 1) / RC_CTA, RC_CTA, 0, s>>>(grp, dq, dd);
 }
