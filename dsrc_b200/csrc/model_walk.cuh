@@ -173,3 +173,121 @@ __global__ void __launch_bounds__(WALK_CTA, 2) k_model_walk(Workspace ws)
         }
     }
 }
+
+// ---- DNA: TDnaRCOrderModeler<order <= 6, 4 symbols> (src/DnaModelerRCO.h:45-62,94-119), one WARP per block. The table -- 4096
+// contexts x 4 x u16 = 32 KiB -- lives in shared memory and the block is walked 32 bases per step as above (match.any on the
+// context, two ballots for the 2-bit symbols, the last lane of a context writes its row back): ~2 warp instructions per base and no
+// CTA barrier, against the bidding rounds of the CTA-wide direct engine (model_dna.cuh). Contexts are built 8 consecutive bases per
+// lane (one 8-byte load, the 6 bases of history come from the neighbouring lane) and transposed to row order through shared memory;
+// the table-independent part of the 8 rows of a step is computed before the walk so that only `load row, add, store row` is serial.
+#define DWALK_STEP 256
+struct DnaWalkShared {
+    u64 tab[4096];
+    alignas(16) u16 ks[DWALK_STEP];                    // (context << 2) | base
+    u8 claim[4096];                                    // lane that wrote last, per context (collision detection inside a row)
+};
+
+__global__ void __launch_bounds__(32) k_dna_walk(Workspace ws)
+{
+    extern __shared__ __align__(16) u8 walk_smem[];
+    DnaWalkShared& S = *(DnaWalkShared*)walk_smem;
+    const u32 ln = threadIdx.x, lt = (1u << ln) - 1;
+    const u32 limit = (1u << 16) - 8;                  // MaxAccumulatedValue of a 4-symbol coder
+    u32* const queue = ws.model_queue + 3;             // (the quality walk launch of this batch has drained its counter: reset below)
+    const u32 ord = ws.dna_order > 6 ? 6u : ws.dna_order, mask = (1u << (2 * ord)) - 1;
+    for (;;) {
+        u32 blk = 0;
+        if (ln == 0) blk = atomicAdd(queue, 1u);
+        blk = __shfl_sync(FULL, blk, 0);
+        if (blk >= ws.n_blocks) break;
+        const BlockDesc& d = ws.desc[blk];
+        BlockState& st = ws.state[blk];
+        bool take = st.status == ST_OK && ws.dna_order <= 6 && st.d_count > 0 && st.d_count <= 4 && st.d_total > 0;
+        for (u32 i = 4; i < 20 && take; ++i) if (st.dfreq[i]) take = false;       // the other launch reports it
+        __syncwarp();
+        if (ln == 0) { st.pad[1] = (u8)((st.pad[1] & 1u) | (take ? 2u : 0u)); if (take) st.d_scheme = 0; }
+        if (!take) continue;
+        const u32 M = st.d_total;
+        for (u32 j = ln; j <= mask; j += 32) S.tab[j] = 0x0001000100010001ull;
+        __syncwarp();
+        const u8* sq = ws.dcat + d.sym_base;
+        uint2* const trip = (uint2*)(ws.trip_d + d.sym_base);
+        u64 cur = 8 * ln < M ? *(const u64*)(sq + 8 * ln) : 0ull;         // the arena has slack behind M
+        u32 carry = 0;                                                    // packed bases of the previous step's last lane
+        for (u32 t0 = 0; t0 < M; t0 += DWALK_STEP) {
+            const u32 i = t0 + 8 * ln;
+            const u64 nxt = i + DWALK_STEP < M ? *(const u64*)(sq + i + DWALK_STEP) : 0ull;
+            // 8 bases -> 16 bits, oldest in the low bits
+            const u32 lo = (u32)cur, hi = (u32)(cur >> 32);
+            u32 p16 = ((lo & 3u) | ((lo >> 6) & 0xCu) | ((lo >> 12) & 0x30u) | ((lo >> 18) & 0xC0u)) |
+                      (((hi & 3u) | ((hi >> 6) & 0xCu) | ((hi >> 12) & 0x30u) | ((hi >> 18) & 0xC0u)) << 8);
+            if (i + 8 > M) p16 &= i < M ? (1u << (2 * (M - i))) - 1 : 0u;
+            u32 prev = __shfl_up_sync(FULL, p16, 1);
+            if (ln == 0) prev = carry;
+            carry = __shfl_sync(FULL, p16, 31);
+            const u32 W = (prev >> 4) | (p16 << 12);                      // bases i-6 .. i+7
+            u32 el[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) el[k] = ((((W >> (12 + 2 * k - 2 * ord)) & mask) << 2) | ((W >> (12 + 2 * k)) & 3u)) & 0xFFFFu;
+            *(uint4*)&S.ks[8 * ln] = make_uint4(el[0] | (el[1] << 16), el[2] | (el[3] << 16), el[4] | (el[5] << 16), el[6] | (el[7] << 16));
+            __syncwarp();
+            // ---- the walk. Contexts of DNA rarely collide inside a row of 32 bases and match.any costs a step per distinct value, so
+            // collisions are detected through shared memory first: every lane writes its number to its context's claim cell; if all
+            // lanes read their own number back, every lane is alone with its row (the common case). Otherwise the peers come from
+            // twelve ballots.
+#pragma unroll 1
+            for (u32 j = 0; j < 8; ++j) {
+                if (t0 + 32 * j >= M) break;
+                const u32 e = S.ks[32 * j + ln];
+                const bool valid = t0 + 32 * j + ln < M;
+                const u32 key = valid ? e >> 2 : 0u, s = e & 3u;
+                if (valid) S.claim[key] = (u8)ln;
+                __syncwarp();
+                const u32 won = S.claim[key];
+                const u64 row = S.tab[key];
+                u32 v01 = (u32)row, v23 = (u32)(row >> 32);
+                bool last = valid;
+                if (__ballot_sync(FULL, valid && won != ln)) {
+                    u32 peers = __ballot_sync(FULL, valid);
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) { const u32 m = __ballot_sync(FULL, (key >> k) & 1u); peers &= ((key >> k) & 1u) ? m : ~m; }
+                    const u32 b1 = __ballot_sync(FULL, e & 1u), b2 = __ballot_sync(FULL, e & 2u);
+                    const u32 below = peers & lt;
+                    v01 += 2u * (__popc(below & ~b1 & ~b2) | (__popc(below & b1 & ~b2) << 16));
+                    v23 += 2u * (__popc(below & ~b1 & b2) | (__popc(below & b1 & b2) << 16));
+                    last = valid && (peers >> ln) == 1u;
+                }
+                const u32 p01 = v01 * 0x10001u, p23 = v23 * 0x10001u;    // low half: first counter, high half: sum of the pair
+                const u32 tot = (p01 >> 16) + (p23 >> 16);
+                if (__any_sync(FULL, valid && tot >= limit)) {
+                    // a rescale falls into this row: lane 0 codes it base by base (TSymbolCoderRC::Accumulate / Rescale)
+                    const u32 vm = __ballot_sync(FULL, valid);
+                    for (u32 x = 0; x < 32; ++x) {
+                        const u32 kx = __shfl_sync(FULL, key, x), sx = __shfl_sync(FULL, s, x);
+                        if (!((vm >> x) & 1u)) break;
+                        if (ln == 0) {
+                            unsigned long long rw = S.tab[kx];
+                            u32 f, cum, T;
+                            dna_row_step(rw, sx, f, cum, T);
+                            S.tab[kx] = rw;
+                            trip[t0 + 32 * j + x] = make_uint2(f | (cum << 16), T);
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
+                const u32 pair = (s & 2u) ? v23 : v01;
+                const u32 f = (s & 1u) ? pair >> 16 : pair & 0xFFFFu;
+                const u32 lowp = (s & 2u) ? p23 : p01;
+                const u32 cum = ((s & 2u) ? p01 >> 16 : 0u) + ((s & 1u) ? lowp & 0xFFFFu : 0u);
+                if (valid) trip[t0 + 32 * j + ln] = make_uint2(f | (cum << 16), tot);
+                if (last) {                             // no peer above me: my view plus my own base is the row after this step
+                    const u32 inc = 2u << ((s & 1u) * 16);
+                    S.tab[key] = (u64)(v01 + ((s & 2u) ? 0u : inc)) | ((u64)(v23 + ((s & 2u) ? inc : 0u)) << 32);
+                }
+                __syncwarp();
+            }
+            cur = nxt;
+        }
+    }
+}

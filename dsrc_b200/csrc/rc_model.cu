@@ -499,7 +499,7 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
         // ---- scheme selection. Only thread 0 looks at (and may set) the block's status; everybody else learns the outcome from
         // shared memory after the barrier, so the whole CTA takes the same path through next_block()'s barriers
         if (tid == 0) {
-            S.ok = st.status == ST_OK && !(QUALITY && st.pad[1]);      // pad[1]: the walk engine's launch (model_walk.cuh) has coded the block
+            S.ok = st.status == ST_OK && !(st.pad[1] & (QUALITY ? 1u : 2u));      // pad[1]: the walk engines' launches (model_walk.cuh) have coded the block
             S.M = 0;
             if (!S.ok) {}
             else if (QUALITY) {
@@ -776,7 +776,16 @@ void launch_model_quality(const Workspace& ws, cudaStream_t s, u32 ctas, u64 str
     k_model<true, true><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY, s>>>(ws, stride);
     k_model<true, false><<<model_grid(ws, ctas), DSRC_CTA, MODEL_SMEM_QUALITY_CLASSIC, s>>>(ws, stride);
 }
-void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride) { model_smem_optin(); k_model<false, false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride); }
+void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride)
+{
+    model_smem_optin();
+    {   // 4-symbol blocks at order <= 6: one warp per block, table in shared memory (model_walk.cuh); 6 warps per SM
+        cudaMemsetAsync(ws.model_queue + 3, 0, 4, s);
+        const u32 g = ws.n_blocks < 148u * 6u ? ws.n_blocks : 148u * 6u;
+        k_dna_walk<<<g ? g : 1, 32, sizeof(DnaWalkShared), s>>>(ws);
+    }
+    k_model<false, false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride);
+}
 cudaError_t rc_init_device() { k_rcp_lut<<<65536 / 256, 256>>>(); return cudaDeviceSynchronize(); }
 void launch_rc_encode(const RcGroup& grp, cudaStream_t s)
 {
