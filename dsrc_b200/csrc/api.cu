@@ -83,6 +83,10 @@ struct dsrcgpu_ctx {
     std::string err;
     Slot slots[MAX_SLOTS]; int n_slots = 1;
     DevBuf prof, cursor, dec_arena;
+    // host-buffer calls: the next batch's input travels on a stream of its own into a spare staging buffer while the host still waits
+    // for that batch's slot, so the input link never idles behind a slot; the buffers are swapped when the slot is free
+    DevBuf spare_in[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> copy_ev;     // timers of those copies (collected at the end of the call)
     DevBuf tab, tab_mask; u32 tab_count = 0;         // pool of adaptive-row tables shared by all slots (rc_model.cu: tab_acquire)
     u64 tab_stride = 0;
     u32 model_ctas = 0; u64 model_stride = 0; u32 tag_ctas = 0; u32 q0_ctas = 0; u64 q0_stride = 0;
@@ -204,7 +208,9 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (int i = 0; i < ctx->n_slots; ++i) { if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream); if (ctx->slots[i].stream_r) cudaStreamSynchronize(ctx->slots[i].stream_r); ctx->slots[i].release(); }
-    ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release(); ctx->tab.release(); ctx->tab_mask.release();
+    ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release(); ctx->tab.release(); ctx->tab_mask.release(); ctx->spare_in[0].release(); ctx->spare_in[1].release();
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (cudaEvent_t e : ctx->ev_copy) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->call_a) cudaEventDestroy(ctx->call_a);
     if (ctx->call_b) cudaEventDestroy(ctx->call_b);
@@ -242,9 +248,10 @@ static int ensure_host(dsrcgpu_ctx* ctx, Slot& sl, u32 n)
     if (sl.h_result) cudaFreeHost(sl.h_result);
     if (sl.h_probe) cudaFreeHost(sl.h_probe);
     sl.h_desc = nullptr; sl.h_result = nullptr; sl.h_probe = nullptr; sl.h_cap = 0;
-    CK(cudaHostAlloc((void**)&sl.h_desc, sizeof(BlockDesc) * n, cudaHostAllocDefault));
-    CK(cudaHostAlloc((void**)&sl.h_result, sizeof(BlockResult) * n, cudaHostAllocDefault));
-    CK(cudaHostAlloc((void**)&sl.h_probe, sizeof(BlockProbe) * n, cudaHostAllocDefault));
+    // mapped: the encode scheduler moves these with a kernel (launch_copy_words), not with the copy engines
+    CK(cudaHostAlloc((void**)&sl.h_desc, sizeof(BlockDesc) * n, cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(cudaHostAlloc((void**)&sl.h_result, sizeof(BlockResult) * n, cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(cudaHostAlloc((void**)&sl.h_probe, sizeof(BlockProbe) * n, cudaHostAllocMapped | cudaHostAllocPortable));
     sl.h_cap = n;
     return DSRCGPU_OK;
 }
@@ -296,9 +303,11 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     if (ctx->phase_prof) { if (!ctx->prof.p) { CK(ctx->prof.ensure(64 * 8)); CK(cudaMemsetAsync(ctx->prof.p, 0, 64 * 8, s)); } ws.prof = (u64*)ctx->prof.p; }
 
     // pass 1: count lines / fields so the batch can be laid out exactly
-    CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    void *m_desc = nullptr, *m_probe = nullptr;      // device addresses of the mapped host arrays
+    CK(cudaHostGetDevicePointer(&m_desc, hd, 0)); CK(cudaHostGetDevicePointer(&m_probe, sl.h_probe, 0));
+    launch_copy_words(sl.desc.p, m_desc, sizeof(BlockDesc) * n, s);
     { KTimer t(ctx, &sl, K_COUNT); launch_count_lines(ws, s); }
-    CK(cudaMemcpyAsync(sl.h_probe, sl.probe.p, sizeof(BlockProbe) * n, cudaMemcpyDeviceToHost, s));
+    launch_copy_words(m_probe, sl.probe.p, sizeof(BlockProbe) * n, s);
     CK(cudaEventRecord(sl.ev_probe, s));
     for (;;) {
         const cudaError_t q = cudaEventQuery(sl.ev_probe);
@@ -363,7 +372,7 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     ws.model_queue = (u32*)sl.queue.p;
     ws.tagpool = (u8*)sl.tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
 
-    CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
+    launch_copy_words(sl.desc.p, m_desc, sizeof(BlockDesc) * n, s);
     if (wait_p && ctx->p_serial == 1) CK(cudaStreamWaitEvent(s, wait_p, 0));
     { KTimer t(ctx, &sl, K_PARSE); launch_parse(ws, s); }
     if (ws.calc_crc) { KTimer t(ctx, &sl, K_CRC); launch_crc(ws, s, 0); }
@@ -405,7 +414,7 @@ static int finish_group(dsrcgpu_ctx* ctx, Slot** members, u32 n, cudaEvent_t wai
         { KTimer t(ctx, &sl, K_SIZES, rs); launch_meta_and_sizes(sl.ws, rs, sl.r_out_base, sl.r_cursor); }
         CK(cudaEventRecord(sl.ev_sizes, rs));
         { KTimer t(ctx, &sl, K_GATHER, rs); launch_gather(sl.ws, rs); }
-        CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * sl.cnt, cudaMemcpyDeviceToHost, rs));
+        { void* m_res = nullptr; CK(cudaHostGetDevicePointer(&m_res, sl.h_result, 0)); launch_copy_words(m_res, sl.result.p, sizeof(BlockResult) * sl.cnt, rs); }
         CK(cudaEventRecord(sl.ev_results, rs));
         sl.r_enq = true;
         wait_sizes = sl.r_cursor ? sl.ev_sizes : nullptr;
@@ -415,9 +424,21 @@ static int finish_group(dsrcgpu_ctx* ctx, Slot** members, u32 n, cudaEvent_t wai
     return DSRCGPU_OK;
 }
 
+// timers of the input copies that travelled on the copy stream (call this when they are complete: after the streams that waited for
+// them have been joined); they are listed under slot 0 in the timeline
+static void collect_copy_times(dsrcgpu_ctx* ctx)
+{
+    Slot& s0 = ctx->slots[0];
+    s0.ev_used.insert(s0.ev_used.end(), ctx->copy_ev.begin(), ctx->copy_ev.end());
+    ctx->copy_ev.clear();
+    collect_times(ctx, &s0);
+}
+
 static void abort_all(dsrcgpu_ctx* ctx)
 {
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < ctx->n_slots; ++i) { cudaStreamSynchronize(ctx->slots[i].stream); cudaStreamSynchronize(rstream(ctx->slots[i])); collect_times(ctx, &ctx->slots[i]); ctx->slots[i].busy = false; }
+    collect_copy_times(ctx);
 }
 
 // The CUDA-stream block scheduler (replaces the worker pool + queues of DsrcCompressorMT, src/DsrcOperator.cpp:230-394):
@@ -436,11 +457,17 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         CK(ctx->cursor.ensure(8));
         CK(cudaMemsetAsync(ctx->cursor.p, 0, 8, ctx->slots[0].stream));
     }
-    // batch schedule: uniform batches. (Measured on B200 for host buffers: small first batches -- to start coding before a whole 2 GiB
-    // batch has arrived -- or small last batches -- to shorten the drain -- both LOSE a few percent: the range-coder chains of a batch
-    // take ~10 ms whatever its size, so small batches cost more compute than the fill / drain they save.)
+    // batch schedule: uniform batches. (Measured on B200 for host buffers, where the input link is the bound and the call ends one
+    // batch's coding after the last byte has arrived: cutting the last batch into 2-4 parts (DSRCGPU_TAIL_SPLIT) does not end the call
+    // sooner -- the range-coder chains take ~10 ms whatever the batch size and the parts wait for slots.)
     std::vector<u32> bfirst;
     for (u32 pos = 0; pos < n; pos += ctx->max_inflight) bfirst.push_back(pos);
+    if (!on_device && bfirst.size() >= 2) {
+        const u32 a = bfirst.back(), len = n - a;
+        u32 parts = 1;
+        if (const char* e = getenv("DSRCGPU_TAIL_SPLIT")) parts = (u32)std::max(1, atoi(e));
+        if (len >= 512 * parts) for (u32 k = 1; k < parts; ++k) bfirst.push_back(a + (u32)((u64)len * k / parts));
+    }
     bfirst.push_back(n);
     const u32 nb = (u32)bfirst.size() - 1;
     u64 out_pos = 0;
@@ -500,6 +527,53 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     auto retire_ready = [&](u32 enqueued) {
         while (rc == DSRCGPU_OK && retired < enqueued && ctx->slots[retired % S].r_enq && cudaEventQuery(ctx->slots[retired % S].ev_results) == cudaSuccess) rc = retire(retired++);
     };
+    // host buffers: the input of the next two batches is sent ahead on the copy stream into two spare staging buffers -- one copy per
+    // batch when its blocks are a (near-)contiguous ascending span, packed copies otherwise -- so the input link keeps running while
+    // the host waits for a slot; a batch takes its buffer over (swap with the slot's) when its turn comes
+    struct Staged { u32 batch; int buf; std::vector<u64> offs; };
+    std::vector<Staged> staged;                            // in batch order, at most 2
+    bool spare_free[2] = {true, true};
+    u32 next_stage = 0;
+    auto stage_more = [&]() -> int {
+        while (!on_device && next_stage < nb && (spare_free[0] || spare_free[1])) {
+            if (!ctx->copy_stream) {
+                CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+                for (cudaEvent_t& e : ctx->ev_copy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+            const int k = spare_free[0] ? 0 : 1;
+            DevBuf& buf = ctx->spare_in[k];
+            const u32 first = bfirst[next_stage], cnt = bfirst[next_stage + 1] - first;
+            Staged st; st.batch = next_stage; st.buf = k; st.offs.resize(cnt);
+            u64 lo = blk_off[first], hi = 0, sum = 0; bool asc = true;
+            for (u32 i = 0; i < cnt; ++i) {
+                u64 o = blk_off[first + i]; u32 l = blk_len[first + i];
+                if (i && o < blk_off[first + i - 1] + blk_len[first + i - 1]) asc = false;
+                lo = std::min(lo, o); hi = std::max(hi, o + l); sum += l;
+            }
+            cudaEvent_t ta = nullptr, tb = nullptr;
+            ctx->k_launches[K_H2D]++;
+            if (ctx->profiling) { ta = get_event(ctx); tb = get_event(ctx); cudaEventRecord(ta, ctx->copy_stream); }
+            if (asc && hi - lo <= sum + (u64)cnt * 64) {
+                CK(buf.ensure(hi - lo + 16));
+                CK(cudaMemcpyAsync(buf.p, fastq + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream));
+                for (u32 i = 0; i < cnt; ++i) st.offs[i] = blk_off[first + i] - lo;
+            } else {
+                CK(buf.ensure(sum + (u64)cnt * 16 + 16));
+                u64 p = 0;
+                for (u32 i = 0; i < cnt; ++i) {
+                    CK(cudaMemcpyAsync((u8*)buf.p + p, fastq + blk_off[first + i], blk_len[first + i], cudaMemcpyHostToDevice, ctx->copy_stream));
+                    st.offs[i] = p; p += align_up(blk_len[first + i], 16);
+                }
+            }
+            if (ctx->profiling) { cudaEventRecord(tb, ctx->copy_stream); ctx->copy_ev.push_back({K_H2D, {ta, tb}}); }
+            CK(cudaEventRecord(ctx->ev_copy[k], ctx->copy_stream));
+            spare_free[k] = false;
+            staged.push_back(std::move(st));
+            ++next_stage;
+        }
+        return DSRCGPU_OK;
+    };
+    rc = stage_more();                                     // the first inputs leave before anything else
     for (u32 b = 0; b < nb && rc == DSRCGPU_OK; ++b) {
         Slot& sl = ctx->slots[b % S];
         retire_ready(b);
@@ -520,27 +594,15 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
             for (u32 i = 0; i < cnt; ++i) sl.offs[i] = blk_off[first + i];
             d_out = out; batch_out_cap = out_cap;
         } else {
-            // stage the batch: one copy when the blocks are a (near-)contiguous ascending span, packed copies otherwise
-            u64 lo = blk_off[first], hi = 0, sum = 0; bool asc = true;
-            for (u32 i = 0; i < cnt; ++i) {
-                u64 o = blk_off[first + i]; u32 l = blk_len[first + i];
-                if (i && o < blk_off[first + i - 1] + blk_len[first + i - 1]) asc = false;
-                lo = std::min(lo, o); hi = std::max(hi, o + l); sum += l;
-            }
-            cudaError_t e = cudaSuccess;
-            KTimer tcopy(ctx, &sl, K_H2D);
-            if (asc && hi - lo <= sum + (u64)cnt * 64) {
-                e = sl.in.ensure(hi - lo + 16);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(sl.in.p, fastq + lo, hi - lo, cudaMemcpyHostToDevice, sl.stream);
-                for (u32 i = 0; i < cnt; ++i) sl.offs[i] = blk_off[first + i] - lo;
-            } else {
-                e = sl.in.ensure(sum + (u64)cnt * 16 + 16);
-                u64 p = 0;
-                for (u32 i = 0; i < cnt && e == cudaSuccess; ++i) {
-                    e = cudaMemcpyAsync((u8*)sl.in.p + p, fastq + blk_off[first + i], blk_len[first + i], cudaMemcpyHostToDevice, sl.stream);
-                    sl.offs[i] = p; p += align_up(blk_len[first + i], 16);
-                }
-            }
+            // the batch's input was sent ahead (stage_more): take its buffer over and send the next batch's into the one given back
+            if (staged.empty() || staged.front().batch != b) { ctx->err = "internal: input staging out of step"; rc = DSRCGPU_E_ARG; break; }
+            const int k = staged.front().buf;
+            std::swap(sl.in, ctx->spare_in[k]);
+            sl.offs.swap(staged.front().offs);
+            staged.erase(staged.begin());
+            cudaError_t e = cudaStreamWaitEvent(sl.stream, ctx->ev_copy[k], 0);
+            spare_free[k] = true;
+            if (e == cudaSuccess) { rc = stage_more(); if (rc) break; }
             u64 bound = 0;
             for (u32 i = 0; i < cnt; ++i) bound += (u64)blk_len[first + i] + (blk_len[first + i] >> 1) + 4096;   // generous: DSRC never expands by 1.5x
             if (e == cudaSuccess) e = sl.out.ensure(bound);
@@ -555,7 +617,8 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
                            [&]() -> int { retire_ready(b); return rc; });
         if (rc) break;
         group[n_group++] = &sl;
-        if ((int)n_group >= ctx->rc_group || b + 1 == nb) { rc = close_group(); if (rc) break; }
+        // (host buffers: the input link is the bound, not the GPU -- every batch finishes on its own, which frees its slot sooner)
+        if ((int)n_group >= (on_device ? ctx->rc_group : 1) || b + 1 == nb) { rc = close_group(); if (rc) break; }
         // keep S-1 batches queued behind the one the host waits for
         while (rc == DSRCGPU_OK && retired + (u32)(S - 1) <= b && S > 1 && retired < b) rc = retire(retired++);
     }
@@ -574,6 +637,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     for (int i = 0; i < S; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].stream)); CK(cudaStreamSynchronize(rstream(ctx->slots[i]))); ctx->slots[i].busy = false; }
     CK(cudaEventSynchronize(ctx->call_b));
     cudaEventElapsedTime(&ctx->call_ms, ctx->call_a, ctx->call_b);
+    collect_copy_times(ctx);
     return DSRCGPU_OK;
 }
 

@@ -74,3 +74,18 @@ __global__ void __launch_bounds__(DSRC_CTA) k_gather(Workspace ws)
 
 void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base, u64* cursor) { k_meta_sizes<<<1, DSRC_CTA, 0, s>>>(ws, out_base, (unsigned long long*)cursor); }
 void launch_gather(const Workspace& ws, cudaStream_t s) { k_gather<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }
+
+// Small host <-> device transfers of the scheduler (block descriptors up, layout probes and block results down) as a kernel over
+// MAPPED pinned host memory instead of a cudaMemcpyAsync: a DMA copy of a few hundred KB would queue behind the 2 GiB payload copies
+// of the other batches on the same copy engine, and the host waits for the probe.
+__global__ void k_copy_words(u32* dst, const u32* src, u32 n)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+void launch_copy_words(void* dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    const u32 n = (u32)((bytes + 3) / 4);
+    if (!n) return;
+    const u32 g = (n + 1023) / 1024;
+    k_copy_words<<<g < 296u ? g : 296u, 256, 0, s>>>((u32*)dst, (const u32*)src, n);
+}

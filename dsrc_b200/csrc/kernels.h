@@ -19,6 +19,7 @@ void launch_d0_dna(const Workspace& ws, cudaStream_t s, u8* arena, u64 stride, u
 u64 q0_arena_bytes(u64 max_block_bytes);
 void launch_meta_and_sizes(const Workspace& ws, cudaStream_t s, u64 out_base, u64* cursor);  // StoreMetaData + dense output offsets (first block at out_base, or at *cursor which is then advanced)
 void launch_gather(const Workspace& ws, cudaStream_t s);          // meta|tags|quality|dna -> dense output
+void launch_copy_words(void* dst, const void* src, size_t bytes, cudaStream_t s);   // small transfers over mapped pinned memory (bytes rounded up to 4)
 
 u64 tagpool_bytes_per_block();
 

@@ -50,7 +50,7 @@ run()
 open(TL, "w").close()
 dt = run()
 print("call wall %.1f ms -> %.2f GB/s; device-timed %.1f ms" % (dt * 1e3, nbytes / dt / 1e9, L.dsrcgpu_last_call_ms(ctx)))
-rows = [l.strip().split(",") for l in open(TL) if l.strip()]
+rows = [l.strip().split(",") for l in open(TL, "rb").read().replace(b"\x00", b"").decode().splitlines() if l.count(",") == 3]
 rows = [(int(r[0]), r[1], float(r[2]), float(r[3])) for r in rows]
 rows.sort(key=lambda r: r[2])
 cur = None

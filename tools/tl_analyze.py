@@ -3,7 +3,7 @@ kernel ran alone / beside others.   python tools/tl_analyze.py gpurun_out/tl.csv
 import csv
 import sys
 
-rows = [(int(r[0]), r[1], float(r[2]), float(r[3])) for r in csv.reader(open(sys.argv[1])) if len(r) == 4]
+rows = [(int(r[0]), r[1], float(r[2]), float(r[3])) for r in csv.reader(open(sys.argv[1], "rb").read().replace(b"\x00", b"").decode().splitlines()) if len(r) == 4]
 calls, cur = [], []
 for r in rows:
     if r[1] in ("count_lines", "copy_h2d") and r[2] < 1.0 and cur and max(x[3] for x in cur) > 5:
