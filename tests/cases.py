@@ -64,6 +64,15 @@ def small_cases():
     c.append(("fuzz_long_text_fields_d6_q2", lt, 6, 2, 0))
     c.append(("fuzz_long_text_fields_d0_q0", lt, 0, 0, 0))
     c.append(("fuzz_short_reads_d6_q2", open(os.path.join(GOLDEN_DIR, "fuzz_short_reads.fq"), "rb").read(), 6, 2, 0))
+    # the shared-memory walk engines (csrc/model_walk.cuh: <= 5 quality symbols and one read length; 4-symbol DNA at order <= 6):
+    # random qualities (every lane of a row in another context, 8 position buckets), read lengths that do not divide into the
+    # buckets, hot contexts that rescale inside a bucket, a read length below the engine's minimum (the tile engine takes it)
+    c.append(("walk_randq4_d6_q2", synth.random_quals(1500, seed=36, n_levels=4), 6, 2, 0))
+    c.append(("walk_randq5_d3_q1", synth.random_quals(1200, seed=37, n_levels=5), 3, 1, 0))
+    c.append(("walk_len37_hot_d6_q2", synth.skewed(9000, length=37, seed=118), 6, 2, 0))
+    c.append(("walk_len101_d3_q2", synth.skewed(4000, length=101, seed=119, p_major=0.6), 3, 2, 0))
+    c.append(("walk_len31_d6_q2", synth.skewed(4000, length=31, seed=120, p_major=0.8), 6, 2, 0))
+    c.append(("walk_homopolymer_d6_q1", synth.skewed(3000, length=150, seed=121, p_major=0.995, levels=(2, 37)), 6, 1, 0))
     return c
 
 

@@ -16,7 +16,7 @@ profile = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 inflight = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 L = _lib.lib()
 ctx = C.c_void_p()
-assert L.dsrcgpu_create(C.byref(ctx), 0, C.byref(_lib.Dataset(33, 0, 0)), C.byref(_lib.Settings(6, 2, 0, 0, 0)), 256 << 10, inflight) == 0
+assert L.dsrcgpu_create(C.byref(ctx), 0, C.byref(_lib.Dataset(33, 0, 0)), C.byref(_lib.Settings(6, 2, 0, 0, 0)), 256 << 10, 8192) == 0     # encoder
 nbytes = reads * 372
 d_in = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
 nb = C.c_uint64()
@@ -31,6 +31,9 @@ sizes = np.zeros(n, dtype=np.uint32)
 rc = L.dsrcgpu_encode_blocks_device(ctx, C.c_void_p(d_in.data_ptr()), offs.ctypes.data_as(_lib.u64p), lens.ctypes.data_as(_lib.u32p), None, n,
                                     C.c_void_p(d_arc.data_ptr()), nbytes // 2, sizes.ctypes.data_as(_lib.u32p), None, None)
 assert rc == 0, L.dsrcgpu_last_error(ctx)
+L.dsrcgpu_destroy(ctx)
+ctx = C.c_void_p()
+assert L.dsrcgpu_create(C.byref(ctx), 0, C.byref(_lib.Dataset(33, 0, 0)), C.byref(_lib.Settings(6, 2, 0, 0, 0)), 256 << 10, inflight) == 0  # decoder
 coffs = np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))[:-1]]).astype(np.uint64)
 d_out = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
 osz = np.zeros(n, dtype=np.uint64)

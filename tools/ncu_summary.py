@@ -16,11 +16,12 @@ shutil.copy(launches, os.path.join(prof, tag + "_ncu_launches_bench.csv"))
 rows = [r for r in csv.reader(open(launches)) if len(r) > 14 and r[0].isdigit()]
 agg = {}
 for r in rows:
-    name = r[4].split("(")[0]
+    name = r[4].split("(Workspace")[0].split("(RcGroup")[0].split("(unsigned")[0]
     if name.startswith("void "):
         name = name[5:]
-    if "k_model" in r[4]:
-        name = "k_model<quality>" if "1>" in r[4].split("(Workspace")[0] else "k_model<dna>"
+    if name.startswith("k_model<"):      # <QUALITY, PART>: walk / partition / classic engines are separate launches
+        name = {"k_model<1, 1>": "k_model<quality, partition engine>", "k_model<1, 0>": "k_model<quality, tile engine>",
+                "k_model<0, 0>": "k_model<dna, tile/direct engine>"}.get(name.replace("true", "1").replace("false", "0"), name)
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += float(r[14]) / 1e6
