@@ -345,7 +345,8 @@ def make_roofline(kbase, ktot, kser_step_ms, steps, alg, peak, peak_kind, payloa
     dom = max(kbase.items(), key=lambda kv: kv[1][0]) if kbase else ("none", (0.0, 0))
     dom_ms_per_step = dom[1][0] / steps
     ach = alg.get(dom[0], 0) / (dom_ms_per_step / 1e3) / 1e9 if dom_ms_per_step > 0 else 0.0
-    launches = max(1, dom[1][1] // max(1, steps))
+    # (the model timers bracket several kernels per batch: walk / partition / tile engine launches, each taking its own blocks)
+    launches = max(1, dom[1][1] // max(1, steps) // {"model_quality": 3, "model_dna": 2}.get(dom[0], 1))
     return {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": ach / peak, "traffic": traffic_of(dom[0]),
             "algorithmic_bytes_per_launch": alg.get(dom[0], 0) / launches,
@@ -362,8 +363,9 @@ def make_roofline(kbase, ktot, kser_step_ms, steps, alg, peak, peak_kind, payloa
 def ncu_traffic(kernel):
     """measured DRAM bytes per launch of a kernel family from the committed `ncu --set full` capture (profiles/), or None"""
     import csv
-    pats = {"model_quality": ("r02_ncu_bench_model_full.csv", "k_model<(bool)1, (bool)0>"), "model_dna": ("r02_ncu_bench_model_full.csv", "k_model<(bool)0, (bool)0>"),
-            "model_quality_part": ("r02_ncu_profile1_model_full.csv", "k_model<(bool)1, (bool)1>")}
+    pats = {"model_quality": ("r02_ncu_bench_model_full.csv", "k_model_walk"), "model_dna": ("r02_ncu_bench_model_full.csv", "k_dna_walk"),
+            "rc_encode": ("r02_ncu_bench_model_full.csv", "k_rc_encode"), "preprocess": ("r02_ncu_bench_model_full.csv", "k_preprocess"),
+            "tags": ("r02_ncu_bench_model_full.csv", "k_tags")}
     if kernel not in pats:
         return None
     try:

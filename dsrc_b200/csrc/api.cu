@@ -95,6 +95,10 @@ struct dsrcgpu_ctx {
     float k_ms[K_NUM]; u32 k_launches[K_NUM];
     cudaEvent_t call_a = nullptr, call_b = nullptr; float call_ms = 0;
     bool profiling = true, phase_prof = false;
+    u32 narrow_div = 0;                              // test switch DSRCGPU_NARROW_STREAMS=<d>: narrow arenas of 1/d byte per symbol (forces the retry)
+    bool host_call = false;                          // the call in progress takes host buffers: small transfers go by kernel over mapped memory
+    bool last_overflow = false;                      // the last call failed with ST_OVERFLOW
+    bool wide_streams = false;                       // range-coder stream arenas at 3 bytes per symbol (set after a chain ran out of its 1.25)
     int rc_group = 2;                                // batches whose range-coder chains share one launch (<= n_slots, RC_GROUP_MAX)
     int p_serial = 2;                                // where a batch waits for the previous batch's parallel stage: 0 nowhere, 1 before parse, 2 before the model kernels
 };
@@ -107,9 +111,9 @@ static cudaEvent_t get_event(dsrcgpu_ctx* ctx)
 }
 struct KTimer {
     dsrcgpu_ctx* ctx; Slot* sl; int k; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
-    KTimer(dsrcgpu_ctx* c, Slot* s, int kid, cudaStream_t on = nullptr) : ctx(c), sl(s), k(kid), st(on ? on : s->stream)
+    KTimer(dsrcgpu_ctx* c, Slot* s, int kid, cudaStream_t on = nullptr, u32 kernels = 1) : ctx(c), sl(s), k(kid), st(on ? on : s->stream)
     {
-        ctx->k_launches[k]++;
+        ctx->k_launches[k] += kernels;                 // kernel launches the timer brackets
         if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, st); }
     }
     ~KTimer() { if (ctx->profiling) { cudaEventRecord(b, st); sl->ev_used.push_back({k, {a, b}}); } }
@@ -160,6 +164,7 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     if (const char* e = getenv("DSRCGPU_SLOTS")) ns = atoi(e);
     ctx->n_slots = std::max(1, std::min(ns, (int)MAX_SLOTS));
     if (const char* e = getenv("DSRCGPU_PSERIAL")) ctx->p_serial = atoi(e);
+    if (const char* e = getenv("DSRCGPU_NARROW_STREAMS")) ctx->narrow_div = (u32)std::max(0, atoi(e));
     if (const char* e = getenv("DSRCGPU_RC_GROUP")) ctx->rc_group = atoi(e);
     ctx->rc_group = std::max(1, std::min(ctx->rc_group, std::min((int)RC_GROUP_MAX, std::max(1, ctx->n_slots - 1))));
     // The model launches of successive batches run one after another (DSRCGPU_PSERIAL=2: two model launches side by side only stretch
@@ -265,7 +270,7 @@ static int status_to_error(dsrcgpu_ctx* ctx, u32 status, u32 blk)
     const char* what = "malformed FASTQ block";
     if (status & 0x100) { code = DSRCGPU_E_CAPACITY; what = "output buffer too small"; }
     else if (status == ST_UNSUPPORTED) { code = DSRCGPU_E_UNSUPPORTED; what = "block outside the supported envelope (see DESIGN.md limits)"; }
-    else if (status == ST_OVERFLOW) { code = DSRCGPU_E_UNSUPPORTED; what = "internal stream arena too small for this block"; }
+    else if (status == ST_OVERFLOW) { code = DSRCGPU_E_UNSUPPORTED; what = "internal stream arena too small for this block"; ctx->last_overflow = true; }
     else if (status == ST_CRC) { code = DSRCGPU_E_MALFORMED; what = "CRC32 checksums mismatch."; }      // message of src/DsrcWorker.cpp:60
     snprintf(msg, sizeof(msg), "block %u: %s (status %u)", blk, what, status);
     ctx->err = msg;
@@ -305,9 +310,13 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     // pass 1: count lines / fields so the batch can be laid out exactly
     void *m_desc = nullptr, *m_probe = nullptr;      // device addresses of the mapped host arrays
     CK(cudaHostGetDevicePointer(&m_desc, hd, 0)); CK(cudaHostGetDevicePointer(&m_probe, sl.h_probe, 0));
-    launch_copy_words(sl.desc.p, m_desc, sizeof(BlockDesc) * n, s);
+    // host-buffer calls move the small arrays with a kernel over mapped memory (a DMA copy would queue behind the 2 GiB payload copies
+    // of the other batches); device-resident calls keep the copy engines, which are idle there, while a kernel would wait for an SM
+    // among the persistent model CTAs (measured: -6 %)
+    const bool by_kernel = ctx->host_call;
+    if (by_kernel) launch_copy_words(sl.desc.p, m_desc, sizeof(BlockDesc) * n, s); else CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
     { KTimer t(ctx, &sl, K_COUNT); launch_count_lines(ws, s); }
-    launch_copy_words(m_probe, sl.probe.p, sizeof(BlockProbe) * n, s);
+    if (by_kernel) launch_copy_words(m_probe, sl.probe.p, sizeof(BlockProbe) * n, s); else CK(cudaMemcpyAsync(sl.h_probe, sl.probe.p, sizeof(BlockProbe) * n, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(sl.ev_probe, s));
     for (;;) {
         const cudaError_t q = cudaEventQuery(sl.ev_probe);
@@ -330,8 +339,12 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
         d.stream_base = streams;
         d.stream_cap[0] = 64;
         d.stream_cap[1] = (u32)align_up((u64)d.in_len / 2 + (128u << 10), 16);
-        d.stream_cap[2] = (u32)align_up((u64)d.in_len / 2 * 3 + 256, 16);
-        d.stream_cap[3] = (u32)align_up((u64)d.in_len / 2 * 3 + (256u << 10), 16);
+        // range-coded streams: 1.25 bytes per symbol (the adaptive coder averages below log2(alphabet) bits per symbol; a chain that
+        // runs out reports ST_OVERFLOW and the call is repeated with `wide_streams`: 3 bytes per symbol, more than a symbol can
+        // cost). The -d0 / -q0 coders (bit packing, Huffman tables in the stream) keep the generous bound.
+        const u64 half = (u64)d.in_len / 2, narrow = ctx->narrow_div ? half / ctx->narrow_div : half + half / 4;
+        d.stream_cap[2] = (u32)align_up((ctx->cs.dna_order && !ctx->wide_streams) ? narrow + 512 : half * 3 + 256, 16);
+        d.stream_cap[3] = (u32)align_up((ctx->cs.quality_order && !ctx->wide_streams) ? narrow + 1024 : half * 3 + (256u << 10), 16);
         streams += (u64)d.stream_cap[0] + d.stream_cap[1] + d.stream_cap[2] + d.stream_cap[3];
         if (lines >= (1ull << 32) || recs >= (1ull << 32)) { ctx->err = "batch too large"; return DSRCGPU_E_ARG; }
     }
@@ -372,16 +385,16 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
     ws.model_queue = (u32*)sl.queue.p;
     ws.tagpool = (u8*)sl.tagpool.p; ws.tagpool_stride = tagpool_bytes_per_block();
 
-    launch_copy_words(sl.desc.p, m_desc, sizeof(BlockDesc) * n, s);
+    if (by_kernel) launch_copy_words(sl.desc.p, m_desc, sizeof(BlockDesc) * n, s); else CK(cudaMemcpyAsync(sl.desc.p, hd, sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, s));
     if (wait_p && ctx->p_serial == 1) CK(cudaStreamWaitEvent(s, wait_p, 0));
     { KTimer t(ctx, &sl, K_PARSE); launch_parse(ws, s); }
     if (ws.calc_crc) { KTimer t(ctx, &sl, K_CRC); launch_crc(ws, s, 0); }
     { KTimer t(ctx, &sl, K_PREP); launch_preprocess(ws, s); }
     { KTimer t(ctx, &sl, K_TAGS); launch_tags(ws, s, ctx->tag_ctas); }
     if (wait_p && ctx->p_serial == 2) CK(cudaStreamWaitEvent(s, wait_p, 0));
-    if (rc_q) { KTimer t(ctx, &sl, K_MODEL_Q); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
+    if (rc_q) { KTimer t(ctx, &sl, K_MODEL_Q, nullptr, 3); launch_model_quality(ws, s, ctx->model_ctas, ctx->model_stride); }
     else { KTimer t(ctx, &sl, K_Q0); launch_q0_quality(ws, s, (u8*)sl.q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
-    if (rc_d) { KTimer t(ctx, &sl, K_MODEL_D); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
+    if (rc_d) { KTimer t(ctx, &sl, K_MODEL_D, nullptr, 2); launch_model_dna(ws, s, ctx->model_ctas, ctx->model_stride); }
     else { KTimer t(ctx, &sl, K_D0); launch_d0_dna(ws, s, (u8*)sl.q0_arena.p, ctx->q0_stride, ctx->q0_ctas); }
     CK(cudaEventRecord(sl.ev_pdone, s));
     CK(cudaGetLastError());
@@ -414,7 +427,8 @@ static int finish_group(dsrcgpu_ctx* ctx, Slot** members, u32 n, cudaEvent_t wai
         { KTimer t(ctx, &sl, K_SIZES, rs); launch_meta_and_sizes(sl.ws, rs, sl.r_out_base, sl.r_cursor); }
         CK(cudaEventRecord(sl.ev_sizes, rs));
         { KTimer t(ctx, &sl, K_GATHER, rs); launch_gather(sl.ws, rs); }
-        { void* m_res = nullptr; CK(cudaHostGetDevicePointer(&m_res, sl.h_result, 0)); launch_copy_words(m_res, sl.result.p, sizeof(BlockResult) * sl.cnt, rs); }
+        if (ctx->host_call) { void* m_res = nullptr; CK(cudaHostGetDevicePointer(&m_res, sl.h_result, 0)); launch_copy_words(m_res, sl.result.p, sizeof(BlockResult) * sl.cnt, rs); }
+        else CK(cudaMemcpyAsync(sl.h_result, sl.result.p, sizeof(BlockResult) * sl.cnt, cudaMemcpyDeviceToHost, rs));
         CK(cudaEventRecord(sl.ev_results, rs));
         sl.r_enq = true;
         wait_sizes = sl.r_cursor ? sl.ev_sizes : nullptr;
@@ -452,6 +466,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
     if (!ctx->call_a) { cudaEventCreate(&ctx->call_a); cudaEventCreate(&ctx->call_b); }
     const int S = ctx->n_slots;
+    ctx->host_call = !on_device;
     cudaEventRecord(ctx->call_a, ctx->slots[0].stream);
     if (on_device) {
         CK(ctx->cursor.ensure(8));
@@ -893,17 +908,31 @@ extern "C" uint64_t dsrcgpu_cut_blocks_window(const uint8_t* data, uint64_t size
     return nb;
 }
 
+// a range-coder chain that ran out of its 1.25 bytes per symbol (enqueue_batch): the call is repeated once with the wide arenas, which
+// no chain can outgrow, and the context keeps them
+static int encode_retry(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const u64* blk_off, const u32* blk_len, const u32* blk_tagcap, u32 n,
+                        u8* out, u64 out_cap, u32* out_sizes, u64* raw_sizes, u64* comp_sizes)
+{
+    if (ctx) ctx->last_overflow = false;
+    int rc = encode_impl(ctx, fastq, on_device, blk_off, blk_len, blk_tagcap, n, out, out_cap, out_sizes, raw_sizes, comp_sizes);
+    if (rc == DSRCGPU_E_UNSUPPORTED && ctx->last_overflow && !ctx->wide_streams && (ctx->cs.dna_order || ctx->cs.quality_order)) {
+        ctx->wide_streams = true;
+        rc = encode_impl(ctx, fastq, on_device, blk_off, blk_len, blk_tagcap, n, out, out_cap, out_sizes, raw_sizes, comp_sizes);
+    }
+    return rc;
+}
+
 extern "C" int dsrcgpu_encode_blocks(dsrcgpu_ctx* ctx, const uint8_t* fastq, const uint64_t* blk_off, const uint32_t* blk_len,
                                      const uint32_t* blk_tagcap, uint32_t n, uint8_t* out, uint64_t out_cap,
                                      uint32_t* out_sizes, uint64_t* raw_stream_sizes, uint64_t* comp_stream_sizes)
 {
-    return encode_impl(ctx, fastq, false, blk_off, blk_len, blk_tagcap, n, out, out_cap, out_sizes, raw_stream_sizes, comp_stream_sizes);
+    return encode_retry(ctx, fastq, false, blk_off, blk_len, blk_tagcap, n, out, out_cap, out_sizes, raw_stream_sizes, comp_stream_sizes);
 }
 extern "C" int dsrcgpu_encode_blocks_device(dsrcgpu_ctx* ctx, const uint8_t* d_fastq, const uint64_t* blk_off, const uint32_t* blk_len,
                                             const uint32_t* blk_tagcap, uint32_t n, uint8_t* d_out, uint64_t out_cap,
                                             uint32_t* out_sizes, uint64_t* raw_stream_sizes, uint64_t* comp_stream_sizes)
 {
-    return encode_impl(ctx, d_fastq, true, blk_off, blk_len, blk_tagcap, n, d_out, out_cap, out_sizes, raw_stream_sizes, comp_stream_sizes);
+    return encode_retry(ctx, d_fastq, true, blk_off, blk_len, blk_tagcap, n, d_out, out_cap, out_sizes, raw_stream_sizes, comp_stream_sizes);
 }
 
 // ---- Q1 helpers (pure host) ----

@@ -18,6 +18,9 @@
 
 #define ST_RETRY 4u
 #define DEC_CTA 32
+#ifndef DEC_DNA_PF
+#define DEC_DNA_PF 2                 // rows prefetched ahead of a DNA chain: 1 = the next base's 4 rows (L1), 2 = also the 16 rows two bases ahead (L2)
+#endif
 
 struct BitR {                     // BitMemoryReader (src/BitMemory.h:28-212): bytes, MSB-first bits through an 8-bit window
     const u8* p; u32 size, pos, cur, ncur; bool ovr;
@@ -437,7 +440,10 @@ __device__ __forceinline__ bool dec_quality_cfg(u32 order, u32 scheme, u32& alph
     return true;
 }
 
-__global__ void __launch_bounds__(DEC_CTA) k_dec_quality(Workspace ws, uint2* pool_base, u32 pool_stride, u8* arena, u64 arena_stride, u64 arena_bytes, u32 first_chain)
+#ifndef DEC_Q_MINB
+#define DEC_Q_MINB 1
+#endif
+__global__ void __launch_bounds__(DEC_CTA, DEC_Q_MINB) k_dec_quality(Workspace ws, uint2* pool_base, u32 pool_stride, u8* arena, u64 arena_stride, u64 arena_bytes, u32 first_chain)
 {
     const u32 blk = blockIdx.x * blockDim.x + threadIdx.x;
     if (blk >= ws.n_blocks) return;
@@ -613,9 +619,13 @@ __global__ void __launch_bounds__(DEC_CTA) k_dec_dna(Workspace ws, uint2* pool_b
                 // start fetching them now, the chain is otherwise one DRAM round trip per base
                 const u8* nx1 = rs.base + (u64)((hash << bits) & mask) * rs.slot_bytes;
                 const u8* nx2 = rs.base + (u64)((hash << (2 * bits)) & mask) * rs.slot_bytes;
+#if DEC_DNA_PF >= 1
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(nx1));
+#endif
+#if DEC_DNA_PF >= 2
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(nx2));
                 if (alpha == 8) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx2 + 512));
+#endif
             }
             bool fresh;
             u16* row = rs.row(hash, fresh);

@@ -667,7 +667,11 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_qu
         }
     }
     const u32 M = is_dna ? st.d_total : st.q_total;
-    if ((u64)pos + 3ull * M + 24 > cap) { st.status = ST_OVERFLOW; return; }
+    // the arena holds 1.25 bytes per symbol (api.cu; the adaptive coder stays below log2(alphabet) bits per symbol on average) -- the
+    // chain checks its position once per sector and gives up with ST_OVERFLOW, which makes the host repeat the call with 3 bytes per
+    // symbol (more than a symbol can ever cost: 16 bits)
+    if ((u64)pos + 64 > cap) { st.status = ST_OVERFLOW; return; }
+    const u32 pos_limit = cap - 48;
     // the chain's triples arrive 4 at a time (one 32-byte sector per load) through a per-thread ring of RC_RING sectors in shared memory (cp.async), so
     // ~RC_RING*4 symbols of DRAM latency are covered; its output bytes leave 4 at a time. `range / tot` is the one long-latency
     // instruction of the chain: the reciprocal floor((2^32-1)/tot) of each symbol's total is fetched from a 64 K-entry table
@@ -738,9 +742,11 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_qu
         RC_FETCH(g + RC_RING, so);                                     // refills the slot of sector g (already in registers)
         so = sn;
         RC_STEP(c0.x, c0.y, m0); RC_STEP(c0.z, c0.w, m1); RC_STEP(c1.x, c1.y, m2); RC_STEP(c1.z, c1.w, m3);
+        if (pos > pos_limit) break;                                    // (4 steps put out at most 32 bytes)
     }
+    if (pos > pos_limit) { asm volatile("cp.async.wait_all;" ::: "memory"); st.status = ST_OVERFLOW; return; }
 #undef RC_FETCH
-    for (u32 i = G * 4; i < M; ++i) { const uint2 tr = ((const uint2*)trip)[i]; const u32 m = RC_RCP(tr.y); RC_STEP(tr.x, tr.y, m); }
+    for (u32 i = G * 4; i < M; ++i) { const uint2 tr = ((const uint2*)trip)[i]; const u32 m = RC_RCP(tr.y); RC_STEP(tr.x, tr.y, m); }   // <= 3 steps: < 24 bytes
     for (int k = 0; k < 8; ++k) { RC_PUT_TOP(); low <<= 8; }
     {
         const u32 on = pos & 3u;

@@ -156,3 +156,19 @@ def test_crc32_blocks_match_oracle(d, q):
             assert got == exp
         assert bc.read(got, out_cap=len(data) + 64) == data
         bc.close()
+
+
+def test_narrow_stream_arenas_are_retried_wide(monkeypatch):
+    """the range-coder streams get 1.25 bytes per symbol; a chain that runs out makes the library repeat the call with arenas no chain
+    can outgrow (csrc/api.cu encode_retry). DSRCGPU_NARROW_STREAMS=64 shrinks the first attempt to 1/64 byte per symbol, so every
+    block of these inputs takes the retry -- the result must not change."""
+    monkeypatch.setenv("DSRCGPU_NARROW_STREAMS", "64")
+    for data, d, q in [(synth.illumina(900, seed=41, regime="full"), 6, 2), (synth.random_quals(900, seed=42, n_levels=4), 3, 1)]:
+        chunk = data[:-1]
+        ora = refbind.Oracle(33, 0, d, q)
+        bc = _bc(d, q, 0, len(chunk))
+        for it in range(2):
+            exp, eraw, ecmp = ora.store(chunk)
+            got, graw, gcmp = bc.store(chunk)
+            assert got == exp and graw == eraw and gcmp == ecmp, it
+        bc.close()

@@ -33,6 +33,7 @@ rc = L.dsrcgpu_encode_blocks_device(ctx, C.c_void_p(d_in.data_ptr()), offs.ctype
 assert rc == 0, L.dsrcgpu_last_error(ctx)
 L.dsrcgpu_destroy(ctx)
 ctx = C.c_void_p()
+os.environ.setdefault("DSRCGPU_DEC_BATCH", str(inflight))
 assert L.dsrcgpu_create(C.byref(ctx), 0, C.byref(_lib.Dataset(33, 0, 0)), C.byref(_lib.Settings(6, 2, 0, 0, 0)), 256 << 10, inflight) == 0  # decoder
 coffs = np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))[:-1]]).astype(np.uint64)
 d_out = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
