@@ -64,6 +64,7 @@ struct BlockState {
     u8 pad[2];
     u32 total_size;
     u32 crc[3], crc_expected[3];   // -c: CRC-32 of titles / sequences / qualities (computed; read from the block header)
+    u32 pre_flat;                  // the block was preprocessed by k_preprocess_flat (parse.cu); k_preprocess skips it
 };
 
 // compact per-block result copied back to the host

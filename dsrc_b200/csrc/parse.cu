@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(DSRC_CTA) k_preprocess(Workspace ws)
 {
     const BlockDesc& d = ws.desc[blockIdx.x];
     BlockState& st = ws.state[blockIdx.x];
-    if (st.status != ST_OK) return;
+    if (st.status != ST_OK || st.pre_flat) return;    // pre_flat: k_preprocess_flat has done the block
     const u8* b = ws.in + d.in_off;
     const RecArrays& R = ws.rec;
     const u32 n_rec = st.n_rec, rb = d.rec_base;
@@ -311,6 +311,188 @@ __global__ void __launch_bounds__(DSRC_CTA) k_preprocess(Workspace ws)
     }
 }
 
+// 0x80 in every non-zero byte of x
+__device__ __forceinline__ u32 nz_bytes(u32 x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+
+// ---- k_preprocess_flat: the same work for blocks whose reads all have one length (Illumina) under a range-coded quality model, laid
+// out by POSITION instead of by record. The byte-per-lane kernel above spends 134 warp instructions per 32 symbols; here a thread takes
+// 8 consecutive positions of the block's quality string (its record and offset by one multiply-high), fetches the 8 quality and 8
+// base bytes with aligned 8-byte loads (two pieces where the positions straddle two records), and works on them four at a time
+// inside 32-bit words: A/C/G/T -> index by two byte permutes (any other letter sends the thread's 8 symbols down a per-byte path:
+// ambiguity transfer, RecordsProcessor.cpp:228-233), byte-wise offset removal, change / presence / base counts by byte masks and
+// popcounts. The processed qualities leave as one aligned 8-byte store per thread; the retained bases are compacted across the CTA
+// (exclusive scan of the threads' counts) through a shared staging buffer that keeps the ragged tail for the next 2048 positions,
+// so they leave as aligned 8-byte stores too. Of the per-record arrays only qcat_off is filled: dcat_off, dna_len and trunc_len
+// are never needed for these blocks (their users are the -q0 coders).
+#define FLAT_SYMS (DSRC_CTA * 8)
+__device__ __forceinline__ u64 flat_load8(const u8* b, u32 off, u32 in_len)
+{
+    if (off + 16 <= in_len) {                          // two aligned words hold the 8 bytes
+        const u8* p = b + off;
+        const u32 a = (u32)((uintptr_t)p & 7u);
+        const u64* B = (const u64*)(p - a);
+        u64 v = B[0];
+        if (a) v = (v >> (8 * a)) | (B[1] << (64 - 8 * a));
+        return v;
+    }
+    u64 v = 0;                                         // the block's last bytes: nothing is read beyond them
+    for (u32 j = 0; j < 8 && off + j < in_len; ++j) v |= (u64)b[off + j] << (8 * j);
+    return v;
+}
+__global__ void __launch_bounds__(DSRC_CTA, 4) k_preprocess_flat(Workspace ws)
+{
+    const BlockDesc& d = ws.desc[blockIdx.x];
+    BlockState& st = ws.state[blockIdx.x];
+    if (st.status != ST_OK) return;
+    const u8* b = ws.in + d.in_off;
+    const RecArrays& R = ws.rec;
+    const u32 n_rec = st.n_rec, rb = d.rec_base, tid = threadIdx.x, w = warp_id(), ln = lane_id();
+    __shared__ u32 sm[DSRC_WARPS + 1];
+    __shared__ u32 s_min, s_max, s_rle, s_bad, s_ends2;
+    __shared__ u8 s_qp[256];
+    __shared__ u32 s_df[DSRC_WARPS][20];
+    __shared__ u8 s_lut[256];
+    __shared__ u8 s_last[2][DSRC_CTA + 1];             // [round parity][thread + 1]: last processed quality byte of every thread
+    __shared__ __align__(16) u8 s_stage[2][FLAT_SYMS + 16];
+    s_lut[tid] = (u8)dna_index((u8)tid);
+    s_qp[tid] = 0;
+    for (u32 i = tid; i < DSRC_WARPS * 20; i += DSRC_CTA) (&s_df[0][0])[i] = 0;
+    if (tid == 0) { s_min = 0xFFFFFFFFu; s_max = 0; s_rle = 0; s_bad = 0; s_ends2 = 0; s_last[1][DSRC_CTA] = 255; }
+    __syncthreads();
+    {   // one read length?
+        u32 mn = 0xFFFFFFFFu, mx = 0;
+        for (u32 r = tid; r < n_rec; r += DSRC_CTA) { const u32 l = R.qua_len[rb + r]; mn = min(mn, l); mx = max(mx, l); }
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn); mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if (ln == 0) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); }
+        __syncthreads();
+    }
+    const u32 L = s_max;
+    const u64 total64 = (u64)n_rec * L;
+    if (s_min != L || L < 8 || ws.qua_order == 0 || total64 > d.sym_cap || total64 >= (1u << 22)) { if (tid == 0) st.pre_flat = 0; return; }
+    const u32 q_total = (u32)total64;
+    for (u32 r = tid; r < n_rec; r += DSRC_CTA) R.qcat_off[rb + r] = r * L;      // (the sort engine's position buckets walk the records, rc_model.cu)
+    u8* qcat = ws.qcat + d.sym_base;
+    u8* dcat = ws.dcat + d.sym_base;
+    const u32 magic_L = 0xFFFFFFFFu / L + 1u;          // p / L = umulhi(p, magic) for p < 2^22, L < 2^10 .. (p * (magic * L - 2^32) < 2^32)
+    const u32 qoff4 = ws.qoff * 0x01010101u;
+    u32 cnt1 = 0, cnt2 = 0, cnt3 = 0, cntv = 0, chg = 0, ends2 = 0, bad = 0, sawff = 0;
+    u32 carry = 0;                                     // retained bases written so far
+    for (u32 c0 = 0, it = 0; c0 < q_total; c0 += FLAT_SYMS, ++it) {
+        const u32 p0 = c0 + 8 * tid;
+        const u32 n = p0 < q_total ? min(8u, q_total - p0) : 0u;
+        u64 q8 = 0, k8 = 0; u32 kept = 0;
+        u32 off = 0;
+        if (n) {
+            const u32 r = L < 1024 ? __umulhi(p0, magic_L) : p0 / L;
+            off = p0 - r * L;
+            const u32 n1 = min(8u, L - off);           // symbols of record r; the rest (n - n1, if any) open record r + 1
+            u64 xs = flat_load8(b, R.seq_off[rb + r] + off, d.in_len), xq = flat_load8(b, R.qua_off[rb + r] + off, d.in_len);
+            if (n1 < n) {
+                const u64 m1 = (1ull << (8 * n1)) - 1;
+                xs = (xs & m1) | (flat_load8(b, R.seq_off[rb + r + 1], d.in_len) << (8 * n1));
+                xq = (xq & m1) | (flat_load8(b, R.qua_off[rb + r + 1], d.in_len) << (8 * n1));
+            }
+            const u64 vm = n >= 8 ? ~0ull : (1ull << (8 * n)) - 1;
+            u32 idx[2], q4[2], nb = 0;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const u32 ws_ = (u32)(xs >> (32 * hf)), qw = (u32)(xq >> (32 * hf)), v = (u32)(vm >> (32 * hf));
+                // A 0x41, C 0x43, G 0x47, T 0x54: bits 1..2 tell them apart (A 0, C 1, T 2, G 3); two byte permutes give the letter that code
+                // stands for (compared with the input) and the index A0 G1 C2 T3
+                const u32 c = (ws_ >> 1) & 0x03030303u;
+                const u32 sel = (c & 3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
+                nb |= (__byte_perm(0x47544341u, 0u, sel) ^ ws_) & v;
+                idx[hf] = __byte_perm(0x01030200u, 0u, sel) & v;
+                q4[hf] = (((qw | 0x80808080u) - (qoff4 & 0x7F7F7F7Fu)) ^ ((qw ^ ~qoff4) & 0x80808080u)) & v;    // byte-wise qua - offset (wrapping)
+            }
+            if (nb == 0) {
+                q8 = ((u64)q4[1] << 32) | q4[0]; k8 = ((u64)idx[1] << 32) | idx[0]; kept = n;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const u32 vb = (u32)(vm >> (32 * hf)) & 0x01010101u, b0 = idx[hf], b1 = idx[hf] >> 1;
+                    cnt1 += __popc(b0 & ~b1 & vb); cnt2 += __popc(~b0 & b1 & vb); cnt3 += __popc(b0 & b1 & vb); cntv += __popc(vb);
+                }
+            } else {
+                // some letter is not A/C/G/T: symbol by symbol (LUT, ambiguity transfer, compaction inside the thread)
+                for (u32 j = 0; j < n; ++j) {
+                    const u32 s = s_lut[(u32)(xs >> (8 * j)) & 255u];
+                    u32 q = (u8)(((u32)(xq >> (8 * j)) & 255u) - ws.qoff);
+                    if (s == 255) bad = 1;
+                    if (s > 3 && q < 7) q = (u8)(q + (128 + ((s - 3 + 1) << 3) - 16));      // RecordsProcessor.cpp:228-233: the base moves into the quality
+                    else if (s < 20) { k8 |= (u64)s << (8 * kept); ++kept; atomicAdd(&s_df[w][s], 1u); }
+                    q8 |= (u64)q << (8 * j);
+                }
+            }
+            *(u64*)(qcat + p0) = q8;                   // aligned; the arena has slack behind q_total
+        }
+        s_last[it & 1][tid + 1] = n ? (u8)(q8 >> (8 * (n - 1))) : (u8)255;
+        // position of every thread's retained bases (the scan's barriers also publish s_last)
+        u32 total, ex = block_excl_sum(kept, sm, &total);
+        if (n) {
+            // changes against the previous symbol (255 before a record's first), presence of the quality bytes, records ending with a 2
+            u64 prev = (q8 << 8) | (tid ? s_last[it & 1][tid] : s_last[(it + 1) & 1][DSRC_CTA]);     // thread 0: the previous round's last thread
+            const u32 js = off ? L - off : 0u;            // first record start inside these 8 positions (>= 8: none)
+            if (js < 8) prev |= 0xFFull << (8 * js);
+            const u64 x = q8 ^ prev;
+            u32 m0 = nz_bytes((u32)x), m1 = nz_bytes((u32)(x >> 32));
+            if (n < 8) { const u64 vmz = ((1ull << (8 * n)) - 1) & 0x8080808080808080ull; m0 &= (u32)vmz; m1 &= (u32)(vmz >> 32); }
+            chg += __popc(m0) + __popc(m1);
+            for (u64 m = ((u64)m1 << 32) | m0; m; m &= m - 1) { const u32 bit = __ffsll((long long)m) - 1; s_qp[(u32)(q8 >> (bit - 7)) & 255u] = 1; }
+            const u32 je = L - 1 - off;                   // the record's last symbol, if inside
+            if (je < n) { const u32 ql = (u32)(q8 >> (8 * je)) & 255u; ends2 += ql == 2; }
+            if (nz_bytes(~(u32)q8) != 0x80808080u || nz_bytes(~(u32)(q8 >> 32)) != 0x80808080u) sawff = 1;       // a symbol 255: leave the block to k_preprocess
+        }
+        {
+            u8* stage = s_stage[it & 1];
+            const u32 pad = carry & 7u;
+            for (u32 j = 0; j < kept; ++j) stage[pad + ex + j] = (u8)(k8 >> (8 * j));
+            __syncthreads();
+            const u32 nq = (pad + total + 7) / 8;
+            for (u32 i = tid; i < nq; i += DSRC_CTA) *(u64*)(dcat + (carry - pad) + 8 * i) = *(const u64*)(stage + 8 * i);
+            const u32 npad = (pad + total) & 7u;         // ragged tail: first bytes of the next round's staging buffer
+            if (tid < npad) s_stage[(it + 1) & 1][tid] = stage[pad + total - npad + tid];
+            carry += total;
+        }
+    }
+    __syncthreads();
+    {
+        cnt1 = __reduce_add_sync(0xFFFFFFFFu, cnt1); cnt2 = __reduce_add_sync(0xFFFFFFFFu, cnt2); cnt3 = __reduce_add_sync(0xFFFFFFFFu, cnt3); cntv = __reduce_add_sync(0xFFFFFFFFu, cntv);
+        chg = __reduce_add_sync(0xFFFFFFFFu, chg); ends2 = __reduce_add_sync(0xFFFFFFFFu, ends2);
+        bad = __any_sync(0xFFFFFFFFu, bad); sawff = __any_sync(0xFFFFFFFFu, sawff);
+        if (ln == 0) {
+            atomicAdd(&s_df[w][0], cntv - cnt1 - cnt2 - cnt3); atomicAdd(&s_df[w][1], cnt1); atomicAdd(&s_df[w][2], cnt2); atomicAdd(&s_df[w][3], cnt3);
+            atomicAdd(&s_rle, chg); atomicAdd(&s_ends2, ends2);
+            if (bad) s_bad |= 1; if (sawff) s_bad |= 2;
+        }
+    }
+    __syncthreads();
+    if (s_bad & 2) { if (tid == 0) st.pre_flat = 0; return; }            // (a quality byte one below the offset: the per-record rule for it lives in k_preprocess)
+    if (tid < 256) st.qfreq[tid] = s_qp[tid];                            // presence only (nothing downstream uses the counts)
+    if (tid < 20) {
+        u32 f = 0;
+        for (int k = 0; k < DSRC_WARPS; ++k) f += s_df[k][tid];
+        st.dfreq[tid] = f;
+        s_df[0][tid] = f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        u32 qc = 0, dc = 0;
+        for (u32 i = 0; i < 256; ++i) st.qrank[i] = s_qp[i] ? (u8)qc++ : (u8)255;
+        for (u32 i = 0; i < 20; ++i) st.drank[i] = s_df[0][i] ? (u8)dc++ : (u8)255;
+        st.q_count = qc; st.d_count = dc;
+        st.q_total = q_total; st.d_total = carry;
+        // every record's first symbol counts as a change; a record ending with symbol 2 counts one less (RecordsProcessor.cpp:259-260)
+        st.min_len = L; st.max_len = L; st.raw_len = q_total; st.th_len = 0; st.rle_len = s_rle - s_ends2;
+        st.flags = 0;
+        if (s_bad & 1) st.status = ST_UNSUPPORTED;
+        st.pre_flat = 1;
+    }
+}
+
 void launch_count_lines(const Workspace& ws, cudaStream_t s) { k_count_lines<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }
 void launch_parse(const Workspace& ws, cudaStream_t s) { k_parse<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }
-void launch_preprocess(const Workspace& ws, cudaStream_t s) { k_preprocess<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws); }
+void launch_preprocess(const Workspace& ws, cudaStream_t s)
+{
+    k_preprocess_flat<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws);      // blocks with one read length under -q1 / -q2 (sets pre_flat)
+    k_preprocess<<<ws.n_blocks, DSRC_CTA, 0, s>>>(ws);           // every other block
+}
