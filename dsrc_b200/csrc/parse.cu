@@ -329,11 +329,12 @@ __device__ __forceinline__ u64 flat_load8(const u8* b, u32 off, u32 in_len)
 {
     if (off + 16 <= in_len) {                          // two aligned words hold the 8 bytes
         const u8* p = b + off;
-        const u32 a = (u32)((uintptr_t)p & 7u);
-        const u64* B = (const u64*)(p - a);
-        u64 v = B[0];
-        if (a) v = (v >> (8 * a)) | (B[1] << (64 - 8 * a));
-        return v;
+        const u32 a = (u32)((uintptr_t)p & 7u), sh = 8 * (a & 3u);
+        const uint2* B = (const uint2*)(p - a);
+        const uint2 B0 = B[0], B1 = B[1];                // (both inside the block: off + 16 <= in_len)
+        const u32 lo = a < 4 ? __funnelshift_r(B0.x, B0.y, sh) : __funnelshift_r(B0.y, B1.x, sh);
+        const u32 hi = a < 4 ? __funnelshift_r(B0.y, B1.x, sh) : __funnelshift_r(B1.x, B1.y, sh);
+        return ((u64)hi << 32) | lo;
     }
     u64 v = 0;                                         // the block's last bytes: nothing is read beyond them
     for (u32 j = 0; j < 8 && off + j < in_len; ++j) v |= (u64)b[off + j] << (8 * j);
@@ -377,23 +378,33 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_preprocess_flat(Workspace ws)
     const u32 qoff4 = ws.qoff * 0x01010101u;
     u32 cnt1 = 0, cnt2 = 0, cnt3 = 0, cntv = 0, chg = 0, ends2 = 0, bad = 0, sawff = 0;
     u32 carry = 0;                                     // retained bases written so far
+    // the 8 base and 8 quality bytes of positions [p0, p0 + 8), fetched one round ahead of their use (the round is otherwise two
+    // dependent memory round trips -- record offsets, then bytes -- in front of three barriers)
+    auto fetch = [&](u32 p0, u64& xs, u64& xq, u32& off) {
+        xs = 0; xq = 0; off = 0;
+        if (p0 >= q_total) return;
+        const u32 n = min(8u, q_total - p0);
+        const u32 r = L < 1024 ? __umulhi(p0, magic_L) : p0 / L;
+        off = p0 - r * L;
+        const u32 n1 = min(8u, L - off);               // symbols of record r; the rest (n - n1, if any) open record r + 1
+        xs = flat_load8(b, R.seq_off[rb + r] + off, d.in_len); xq = flat_load8(b, R.qua_off[rb + r] + off, d.in_len);
+        if (n1 < n) {
+            const u64 m1 = (1ull << (8 * n1)) - 1;
+            xs = (xs & m1) | (flat_load8(b, R.seq_off[rb + r + 1], d.in_len) << (8 * n1));
+            xq = (xq & m1) | (flat_load8(b, R.qua_off[rb + r + 1], d.in_len) << (8 * n1));
+        }
+    };
+    u64 nxs, nxq; u32 noff;
+    fetch(8 * tid, nxs, nxq, noff);
     for (u32 c0 = 0, it = 0; c0 < q_total; c0 += FLAT_SYMS, ++it) {
         const u32 p0 = c0 + 8 * tid;
         const u32 n = p0 < q_total ? min(8u, q_total - p0) : 0u;
         u64 q8 = 0, k8 = 0; u32 kept = 0;
-        u32 off = 0;
+        const u64 xs = nxs, xq = nxq; const u32 off = noff;
+        fetch(p0 + FLAT_SYMS, nxs, nxq, noff);
         if (n) {
-            const u32 r = L < 1024 ? __umulhi(p0, magic_L) : p0 / L;
-            off = p0 - r * L;
-            const u32 n1 = min(8u, L - off);           // symbols of record r; the rest (n - n1, if any) open record r + 1
-            u64 xs = flat_load8(b, R.seq_off[rb + r] + off, d.in_len), xq = flat_load8(b, R.qua_off[rb + r] + off, d.in_len);
-            if (n1 < n) {
-                const u64 m1 = (1ull << (8 * n1)) - 1;
-                xs = (xs & m1) | (flat_load8(b, R.seq_off[rb + r + 1], d.in_len) << (8 * n1));
-                xq = (xq & m1) | (flat_load8(b, R.qua_off[rb + r + 1], d.in_len) << (8 * n1));
-            }
             const u64 vm = n >= 8 ? ~0ull : (1ull << (8 * n)) - 1;
-            u32 idx[2], q4[2], nb = 0;
+            u32 idx[2], q4[2], amb[2];
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 const u32 ws_ = (u32)(xs >> (32 * hf)), qw = (u32)(xq >> (32 * hf)), v = (u32)(vm >> (32 * hf));
@@ -401,27 +412,37 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_preprocess_flat(Workspace ws)
                 // stands for (compared with the input) and the index A0 G1 C2 T3
                 const u32 c = (ws_ >> 1) & 0x03030303u;
                 const u32 sel = (c & 3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
-                nb |= (__byte_perm(0x47544341u, 0u, sel) ^ ws_) & v;
+                amb[hf] = nz_bytes((__byte_perm(0x47544341u, 0u, sel) ^ ws_) & v);               // 0x80 in every byte that is not A/C/G/T
                 idx[hf] = __byte_perm(0x01030200u, 0u, sel) & v;
                 q4[hf] = (((qw | 0x80808080u) - (qoff4 & 0x7F7F7F7Fu)) ^ ((qw ^ ~qoff4) & 0x80808080u)) & v;    // byte-wise qua - offset (wrapping)
             }
-            if (nb == 0) {
-                q8 = ((u64)q4[1] << 32) | q4[0]; k8 = ((u64)idx[1] << 32) | idx[0]; kept = n;
+            kept = n;
+            u32 drop[2] = {0u, 0u};                      // 0x80 in every byte whose base moves into its quality byte
+            if (amb[0] | amb[1]) {
+                // letters that are not A/C/G/T, one by one: LUT; a low-quality one moves into its quality byte and leaves the base
+                // string (ambiguity transfer, RecordsProcessor.cpp:228-233), the others stay with their index
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                    const u32 vb = (u32)(vm >> (32 * hf)) & 0x01010101u, b0 = idx[hf], b1 = idx[hf] >> 1;
-                    cnt1 += __popc(b0 & ~b1 & vb); cnt2 += __popc(~b0 & b1 & vb); cnt3 += __popc(b0 & b1 & vb); cntv += __popc(vb);
+                    for (u32 m = amb[hf]; m; m &= m - 1) {
+                        const u32 sh = (u32)__ffs((int)m) - 8;                                     // bit offset of the byte
+                        const u32 s = s_lut[((u32)(xs >> (32 * hf)) >> sh) & 255u], q = (q4[hf] >> sh) & 255u;
+                        if (s == 255) bad = 1;
+                        if (s > 3 && q < 7) { q4[hf] = (q4[hf] & ~(255u << sh)) | (((q + (128 + ((s - 3 + 1) << 3) - 16)) & 255u) << sh); drop[hf] |= 0x80u << sh; --kept; }
+                        else { idx[hf] = (idx[hf] & ~(255u << sh)) | ((s & 255u) << sh); if (s < 20) atomicAdd(&s_df[w][s], 1u); else { drop[hf] |= 0x80u << sh; --kept; } }
+                    }
                 }
-            } else {
-                // some letter is not A/C/G/T: symbol by symbol (LUT, ambiguity transfer, compaction inside the thread)
-                for (u32 j = 0; j < n; ++j) {
-                    const u32 s = s_lut[(u32)(xs >> (8 * j)) & 255u];
-                    u32 q = (u8)(((u32)(xq >> (8 * j)) & 255u) - ws.qoff);
-                    if (s == 255) bad = 1;
-                    if (s > 3 && q < 7) q = (u8)(q + (128 + ((s - 3 + 1) << 3) - 16));      // RecordsProcessor.cpp:228-233: the base moves into the quality
-                    else if (s < 20) { k8 |= (u64)s << (8 * kept); ++kept; atomicAdd(&s_df[w][s], 1u); }
-                    q8 |= (u64)q << (8 * j);
-                }
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {             // counts of the plain bases (the others were counted above)
+                const u32 vb = (((u32)(vm >> (32 * hf)) & 0x80808080u) & ~amb[hf]) >> 7, b0 = idx[hf], b1 = idx[hf] >> 1;
+                cnt1 += __popc(b0 & ~b1 & vb); cnt2 += __popc(~b0 & b1 & vb); cnt3 += __popc(b0 & b1 & vb); cntv += __popc(vb);
+            }
+            q8 = ((u64)q4[1] << 32) | q4[0]; k8 = ((u64)idx[1] << 32) | idx[0];
+            for (u64 m = ((u64)drop[1] << 32) | drop[0]; m; ) {          // the moved bases leave the string: close the gaps from the top
+                const u32 sh = 63 - __clzll((long long)m) - 7;
+                const u64 low = sh ? (1ull << sh) - 1 : 0ull;
+                k8 = (k8 & low) | ((k8 >> 8) & ~low);
+                m &= ~(0x80ull << sh);
             }
             *(u64*)(qcat + p0) = q8;                   // aligned; the arena has slack behind q_total
         }
@@ -430,22 +451,27 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_preprocess_flat(Workspace ws)
         u32 total, ex = block_excl_sum(kept, sm, &total);
         if (n) {
             // changes against the previous symbol (255 before a record's first), presence of the quality bytes, records ending with a 2
-            u64 prev = (q8 << 8) | (tid ? s_last[it & 1][tid] : s_last[(it + 1) & 1][DSRC_CTA]);     // thread 0: the previous round's last thread
+            const u32 before = tid ? s_last[it & 1][tid] : s_last[(it + 1) & 1][DSRC_CTA];          // thread 0: the previous round's last thread
+            const u32 qlo = (u32)q8, qhi = (u32)(q8 >> 32);
+            u32 plo = __byte_perm(qlo, before, 0x2104), phi = __byte_perm(qhi, qlo, 0x2107);         // the symbols one position earlier
             const u32 js = off ? L - off : 0u;            // first record start inside these 8 positions (>= 8: none)
-            if (js < 8) prev |= 0xFFull << (8 * js);
-            const u64 x = q8 ^ prev;
-            u32 m0 = nz_bytes((u32)x), m1 = nz_bytes((u32)(x >> 32));
+            if (js < 4) plo |= 255u << (8 * js); else if (js < 8) phi |= 255u << (8 * (js - 4));
+            u32 m0 = nz_bytes(qlo ^ plo), m1 = nz_bytes(qhi ^ phi);
             if (n < 8) { const u64 vmz = ((1ull << (8 * n)) - 1) & 0x8080808080808080ull; m0 &= (u32)vmz; m1 &= (u32)(vmz >> 32); }
             chg += __popc(m0) + __popc(m1);
-            for (u64 m = ((u64)m1 << 32) | m0; m; m &= m - 1) { const u32 bit = __ffsll((long long)m) - 1; s_qp[(u32)(q8 >> (bit - 7)) & 255u] = 1; }
+            for (u32 m = m0; m; m &= m - 1) s_qp[(qlo >> ((u32)__ffs((int)m) - 8)) & 255u] = 1;
+            for (u32 m = m1; m; m &= m - 1) s_qp[(qhi >> ((u32)__ffs((int)m) - 8)) & 255u] = 1;
             const u32 je = L - 1 - off;                   // the record's last symbol, if inside
             if (je < n) { const u32 ql = (u32)(q8 >> (8 * je)) & 255u; ends2 += ql == 2; }
-            if (nz_bytes(~(u32)q8) != 0x80808080u || nz_bytes(~(u32)(q8 >> 32)) != 0x80808080u) sawff = 1;       // a symbol 255: leave the block to k_preprocess
+            if (nz_bytes(~qlo) != 0x80808080u || nz_bytes(~qhi) != 0x80808080u) sawff = 1;       // a symbol 255: leave the block to k_preprocess
         }
         {
             u8* stage = s_stage[it & 1];
             const u32 pad = carry & 7u;
-            for (u32 j = 0; j < kept; ++j) stage[pad + ex + j] = (u8)(k8 >> (8 * j));
+            u8* mine = stage + pad + ex;
+            const u32 klo = (u32)k8, khi = (u32)(k8 >> 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { if ((u32)j < kept) mine[j] = (u8)(klo >> (8 * j)); if ((u32)j + 4 < kept) mine[j + 4] = (u8)(khi >> (8 * j)); }
             __syncthreads();
             const u32 nq = (pad + total + 7) / 8;
             for (u32 i = tid; i < nq; i += DSRC_CTA) *(u64*)(dcat + (carry - pad) + 8 * i) = *(const u64*)(stage + 8 * i);

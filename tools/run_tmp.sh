@@ -1,1 +1,3 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_archive.py tests/test_gpu_decode.py tests/test_gpu_shim.py tests/test_fuzz.py -m gpu -x -q 2>&1 | tail -5 > gpurun_out/r2s_parity.log; cat gpurun_out/r2s_parity.log
+python -m pytest tests/test_gpu_parity.py tests/test_fuzz.py tests/test_gpu_archive.py -m gpu -x -q 2>&1 | tail -3
+bash tools/ab.sh 0 stock 2>&1 | grep -E "==|call|preprocess"
+python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --no-decode --no-serial --no-extras > gpurun_out/sw_flat.json 2> gpurun_out/sw_flat.err; python -c "import json;d=json.load(open('gpurun_out/sw_flat.json'));print(round(d['value']),{k:round(v) for k,v in d['roofline']['kernel_ms_per_step'].items()})"
