@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(WALK_CTA, 2) k_model_walk(Workspace ws)
                 if (__any_sync(FULL, valid && tot >= limit)) {
                     // a rescale falls into this row: lane 0 codes it symbol by symbol (TSymbolCoderRC::Accumulate / Rescale)
                     const u32 vm = __ballot_sync(FULL, valid);
+                    __syncwarp();                        // every lane has read its row
                     for (u32 x = 0; x < 32; ++x) {
                         const u32 kx = __shfl_sync(FULL, key, x), sx = __shfl_sync(FULL, s, x), ix = __shfl_sync(FULL, idx, x);
                         if (!((vm >> x) & 1u)) break;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(WALK_CTA, 2) k_model_walk(Workspace ws)
                 u32 cum = base2 + ((s & 1u) ? lowp & 0xFFFFu : 0u);
                 if (s & 4u) { f = v4; cum = sum03; }
                 if (valid) trip[idx] = make_uint2(f | (cum << 16), tot);
+                __syncwarp();                            // every lane has its row: the rows may change
                 if (valid && (peers >> ln) == 1u) {      // no peer above me: my view plus my own symbol is the row after this step
                     const u32 inc = (s & 4u) ? 0u : 2u << ((s & 1u) * 16);
                     tab[key] = (u64)(v01 + ((s & 2u) ? 0u : inc)) | ((u64)(v23 + ((s & 2u) ? inc : 0u)) << 32);
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(32) k_dna_walk(Workspace ws)
                 if (__any_sync(FULL, valid && tot >= limit)) {
                     // a rescale falls into this row: lane 0 codes it base by base (TSymbolCoderRC::Accumulate / Rescale)
                     const u32 vm = __ballot_sync(FULL, valid);
+                    __syncwarp();                        // every lane has read its row
                     for (u32 x = 0; x < 32; ++x) {
                         const u32 kx = __shfl_sync(FULL, key, x), sx = __shfl_sync(FULL, s, x);
                         if (!((vm >> x) & 1u)) break;
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(32) k_dna_walk(Workspace ws)
                 const u32 lowp = (s & 2u) ? p23 : p01;
                 const u32 cum = ((s & 2u) ? p01 >> 16 : 0u) + ((s & 1u) ? lowp & 0xFFFFu : 0u);
                 if (valid) trip[t0 + 32 * j + ln] = make_uint2(f | (cum << 16), tot);
+                __syncwarp();                            // every lane has its row: the rows may change
                 if (last) {                             // no peer above me: my view plus my own base is the row after this step
                     const u32 inc = 2u << ((s & 1u) * 16);
                     S.tab[key] = (u64)(v01 + ((s & 2u) ? 0u : inc)) | ((u64)(v23 + ((s & 2u) ? inc : 0u)) << 32);

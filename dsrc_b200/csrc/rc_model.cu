@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cstddef>
+#include <cstdlib>
 
 #ifndef MODEL_REGS
 #define MODEL_REGS 56
@@ -787,7 +788,9 @@ void launch_model_dna(const Workspace& ws, cudaStream_t s, u32 ctas, u64 stride)
     model_smem_optin();
     {   // 4-symbol blocks at order <= 6: one warp per block, table in shared memory (model_walk.cuh); 6 warps per SM
         cudaMemsetAsync(ws.model_queue + 3, 0, 4, s);
-        const u32 g = ws.n_blocks < 148u * 6u ? ws.n_blocks : 148u * 6u;
+        static int per_sm = 0;
+        if (!per_sm) { const char* e = getenv("DSRCGPU_DWALK_PER_SM"); per_sm = e ? atoi(e) : 6; if (per_sm < 1) per_sm = 1; }
+        const u32 g = ws.n_blocks < 148u * (u32)per_sm ? ws.n_blocks : 148u * (u32)per_sm;
         k_dna_walk<<<g ? g : 1, 32, sizeof(DnaWalkShared), s>>>(ws);
     }
     k_model<false, false><<<model_grid(ws, ctas), DSRC_CTA, sizeof(ModelShared), s>>>(ws, stride);
