@@ -783,7 +783,16 @@ def main():
         del d_dec
         torch.cuda.empty_cache()
         # through host buffers: compressed blocks in pinned host memory, FASTQ out in pinned host memory
-        nh = min(n, 16384)
+        # the whole shard when the box's RAM allows (its share per rank, as in the e2e leg): a small sample's chains are latency-bound
+        try:
+            import psutil
+            h_budget = int(psutil.virtual_memory().total * 0.5 / max(1, world))
+        except Exception:
+            h_budget = 32 << 30
+        nh = n
+        if dbytes + comp_bytes > h_budget:
+            ends_ = np.cumsum(lens.astype(np.uint64) + np.uint64(1))
+            nh = max(1, int(np.searchsorted(ends_, np.uint64(h_budget * 3 // 4), side="right")))
         cbytes = int(sizes[:nh].astype(np.uint64).sum())
         hbytes = int(lens[:nh].astype(np.uint64).sum()) + nh
         h_c = torch.empty(cbytes, dtype=torch.uint8, pin_memory=True)

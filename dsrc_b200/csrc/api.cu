@@ -86,6 +86,7 @@ struct dsrcgpu_ctx {
     // host-buffer calls: the next batch's input travels on a stream of its own into a spare staging buffer while the host still waits
     // for that batch's slot, so the input link never idles behind a slot; the buffers are swapped when the slot is free
     DevBuf spare_in[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    DevBuf dec_out2;                                 // decode with host buffers: second output staging buffer (a batch's output copy runs beside the next batch's chains)
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> copy_ev;     // timers of those copies (collected at the end of the call)
     DevBuf tab, tab_mask; u32 tab_count = 0;         // pool of adaptive-row tables shared by all slots (rc_model.cu: tab_acquire)
     u64 tab_stride = 0;
@@ -213,7 +214,7 @@ extern "C" void dsrcgpu_destroy(dsrcgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (int i = 0; i < ctx->n_slots; ++i) { if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream); if (ctx->slots[i].stream_r) cudaStreamSynchronize(ctx->slots[i].stream_r); ctx->slots[i].release(); }
-    ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release(); ctx->tab.release(); ctx->tab_mask.release(); ctx->spare_in[0].release(); ctx->spare_in[1].release();
+    ctx->prof.release(); ctx->cursor.release(); ctx->dec_arena.release(); ctx->tab.release(); ctx->tab_mask.release(); ctx->spare_in[0].release(); ctx->spare_in[1].release(); ctx->dec_out2.release();
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (cudaEvent_t e : ctx->ev_copy) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -718,8 +719,17 @@ static int decode_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* i
     return DSRCGPU_OK;
 }
 
+static int decode_run(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u64* blk_off, const u32* blk_len, u32 n,
+                      u8* out, u64 out_cap, u64* out_sizes);
 static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u64* blk_off, const u32* blk_len, u32 n,
                        u8* out, u64 out_cap, u64* out_sizes)
+{
+    const int rc = decode_run(ctx, dsrc, on_device, blk_off, blk_len, n, out, out_cap, out_sizes);
+    if (rc && ctx && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);     // no copy into the caller's buffer outlives a failed call
+    return rc;
+}
+static int decode_run(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u64* blk_off, const u32* blk_len, u32 n,
+                      u8* out, u64 out_cap, u64* out_sizes)
 {
     if (!ctx) return DSRCGPU_E_ARG;
     if (!dsrc || !blk_off || !blk_len || !out || !out_sizes) { ctx->err = "null argument"; return DSRCGPU_E_ARG; }
@@ -748,6 +758,7 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
     per_batch0 = (n + (n + per_batch0 - 1) / per_batch0 - 1) / ((n + per_batch0 - 1) / per_batch0);   // equal batches: the chains of a small last batch would be latency-bound
     std::vector<u32> idx, status, sizes, retry; std::vector<u64> offs, ooffs;
     u64 out_pos = 0;
+    u32 dec_batches = 0;
     for (u32 first = 0; first < n;) {
         const u32 per_batch = start_tier == 0 ? per_batch0 : (u32)std::max<u64>(1, std::min<u64>(dec_batch, budget / (tiers[start_tier] + (u64)pools[start_tier] * 8)));
         const u32 cnt = std::min(per_batch, n - first);
@@ -780,8 +791,15 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
                 const u32 chunk = blk_len[first + i] >= 16 ? (((u32)b[12] << 24) | ((u32)b[13] << 16) | ((u32)b[14] << 8) | b[15]) : 0;
                 ooffs[i] = batch_bytes; batch_bytes += (u64)chunk + 1;
             }
-            CK(sl.out.ensure(batch_bytes + 16));
-            d_out = (u8*)sl.out.p; cap = batch_bytes;
+            // two staging buffers in turn: the copy of a batch's FASTQ to the host runs on the copy stream while the next batch is decoded
+            DevBuf& ob = (dec_batches & 1u) ? ctx->dec_out2 : sl.out;
+            if (!ctx->copy_stream) {
+                CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+                for (cudaEvent_t& e : ctx->ev_copy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
+            if (dec_batches >= 2) CK(cudaEventSynchronize(ctx->ev_copy[dec_batches & 1u]));      // its previous contents have left
+            CK(ob.ensure(batch_bytes + 16));
+            d_out = (u8*)ob.p; cap = batch_bytes;
             if (out_pos + batch_bytes > out_cap) { ctx->err = "output buffer too small"; return DSRCGPU_E_CAPACITY; }
         } else {
             // device-resident input: one probe launch reads every block header (ReadMetaData) for the output offsets
@@ -823,12 +841,17 @@ static int decode_impl(dsrcgpu_ctx* ctx, const u8* dsrc, bool on_device, const u
         }
         for (u32 i = 0; i < cnt; ++i) out_sizes[first + i] = sizes[i];
         if (!on_device) {
-            CK(cudaMemcpyAsync(out + out_pos, d_out, batch_bytes, cudaMemcpyDeviceToHost, sl.stream));
-            CK(cudaStreamSynchronize(sl.stream));
+            // (decode_batch has waited for the batch's kernels)
+            CK(cudaMemcpyAsync(out + out_pos, d_out, batch_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_copy[dec_batches & 1u], ctx->copy_stream));
         }
+        ++dec_batches;
         out_pos += batch_bytes;
         if (start_tier < 1 && n_retry0 * 2 > cnt) start_tier = 1;
         first += cnt;
+    }
+    if (!on_device && ctx->copy_stream) {                 // the last output copies
+        CK(cudaStreamSynchronize(ctx->copy_stream));
     }
     cudaEventRecord(ctx->call_b, sl.stream);
     CK(cudaEventSynchronize(ctx->call_b));
