@@ -344,8 +344,8 @@ static int enqueue_batch(dsrcgpu_ctx* ctx, Slot& sl, const u8* d_in, const u32* 
         // runs out reports ST_OVERFLOW and the call is repeated with `wide_streams`: 3 bytes per symbol, more than a symbol can
         // cost). The -d0 / -q0 coders (bit packing, Huffman tables in the stream) keep the generous bound.
         const u64 half = (u64)d.in_len / 2, narrow = ctx->narrow_div ? half / ctx->narrow_div : half + half / 4;
-        d.stream_cap[2] = (u32)align_up((ctx->cs.dna_order && !ctx->wide_streams) ? narrow + 512 : half * 3 + 256, 16);
-        d.stream_cap[3] = (u32)align_up((ctx->cs.quality_order && !ctx->wide_streams) ? narrow + 1024 : half * 3 + (256u << 10), 16);
+        d.stream_cap[2] = (u32)align_up((ctx->cs.dna_order && !ctx->wide_streams) ? narrow + 1024 : half * 3 + 256, 16);
+        d.stream_cap[3] = (u32)align_up((ctx->cs.quality_order && !ctx->wide_streams) ? narrow + 2048 : half * 3 + (256u << 10), 16);
         streams += (u64)d.stream_cap[0] + d.stream_cap[1] + d.stream_cap[2] + d.stream_cap[3];
         if (lines >= (1ull << 32) || recs >= (1ull << 32)) { ctx->err = "batch too large"; return DSRCGPU_E_ARG; }
     }

@@ -669,10 +669,11 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_qu
     }
     const u32 M = is_dna ? st.d_total : st.q_total;
     // the arena holds 1.25 bytes per symbol (api.cu; the adaptive coder stays below log2(alphabet) bits per symbol on average) -- the
-    // chain checks its position once per sector and gives up with ST_OVERFLOW, which makes the host repeat the call with 3 bytes per
-    // symbol (more than a symbol can ever cost: 16 bits)
-    if ((u64)pos + 64 > cap) { st.status = ST_OVERFLOW; return; }
-    const u32 pos_limit = cap - 48;
+    // chain checks its position every RC_CHECK sectors (outside the inner loop: a test per sector cost 11 %) and gives up with
+    // ST_OVERFLOW, which makes the host repeat the call with 3 bytes per symbol (more than a symbol can ever cost: 16 bits)
+    constexpr u32 RC_CHECK = 32;                       // 32 sectors = 128 steps put out at most 512 bytes
+    if ((u64)pos + 640 > cap) { st.status = ST_OVERFLOW; return; }
+    const u32 pos_limit = cap - 600;
     // the chain's triples arrive 4 at a time (one 32-byte sector per load) through a per-thread ring of RC_RING sectors in shared memory (cp.async), so
     // ~RC_RING*4 symbols of DRAM latency are covered; its output bytes leave 4 at a time. `range / tot` is the one long-latency
     // instruction of the chain: the reciprocal floor((2^32-1)/tot) of each symbol's total is fetched from a 64 K-entry table
@@ -731,7 +732,9 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_qu
     uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;                        // the next sector's 4 triples, (lo, hi) word pairs, one sector ahead in registers
     if (G) { n0 = *(const uint4*)rp; n1 = *(const uint4*)(rp + HALF); mn0 = RC_RCP(n0.y); mn1 = RC_RCP(n0.w); mn2 = RC_RCP(n1.y); mn3 = RC_RCP(n1.w); }
     u32 so = 0;                                                        // byte offset of the ring slot of sector g
-    for (u32 g = 0; g < G; ++g) {
+    for (u32 g0 = 0; g0 < G && pos <= pos_limit; g0 += RC_CHECK) {
+    const u32 g1 = min(G, g0 + RC_CHECK);
+    for (u32 g = g0; g < g1; ++g) {
         const u32 sn = so + SLOT == RC_RING * SLOT ? 0u : so + SLOT;
         const uint4 c0 = n0, c1 = n1;
         const u32 m0 = mn0, m1 = mn1, m2 = mn2, m3 = mn3;
@@ -743,7 +746,7 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_qu
         RC_FETCH(g + RC_RING, so);                                     // refills the slot of sector g (already in registers)
         so = sn;
         RC_STEP(c0.x, c0.y, m0); RC_STEP(c0.z, c0.w, m1); RC_STEP(c1.x, c1.y, m2); RC_STEP(c1.z, c1.w, m3);
-        if (pos > pos_limit) break;                                    // (4 steps put out at most 32 bytes)
+    }
     }
     if (pos > pos_limit) { asm volatile("cp.async.wait_all;" ::: "memory"); st.status = ST_OVERFLOW; return; }
 #undef RC_FETCH

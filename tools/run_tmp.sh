@@ -1,1 +1,3 @@
-python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --no-serial --no-extras > gpurun_out/sw_dec.json 2> gpurun_out/sw_dec.err; tail -3 gpurun_out/sw_dec.err; python -c "import json;d=json.load(open('gpurun_out/sw_dec.json'));print(round(d['value']),d['decode']['value'],d['decode']['e2e'])"
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_archive.py -m gpu -x -q 2>&1 | tail -2
+bash tools/ab.sh 0 stock 2>&1 | grep -E "==|call|rc_encode"
+python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --no-decode --no-serial --no-extras > gpurun_out/sw_rc.json 2> gpurun_out/sw_rc.err; python -c "import json;d=json.load(open('gpurun_out/sw_rc.json'));print(round(d['value']),{k:round(v) for k,v in d['roofline']['kernel_ms_per_step'].items()})"
