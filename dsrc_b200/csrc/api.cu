@@ -415,7 +415,8 @@ static int finish_group(dsrcgpu_ctx* ctx, Slot** members, u32 n, cudaEvent_t wai
     if (rc_q || rc_d) {
         RcGroup grp{}; grp.n = n;
         for (u32 k = 0; k < n; ++k) { grp.ws[k] = members[k]->ws; if (members[k] != &last || r != last.stream) CK(cudaStreamWaitEvent(r, members[k]->ev_pdone, 0)); }
-        { KTimer t(ctx, &last, K_RC, r); launch_rc_encode(grp, r); }
+        static const bool skip_rc = getenv("DSRCGPU_DEV_SKIP_RC") != nullptr;      // developer timing experiment: output is wrong without the chains
+        if (!skip_rc) { KTimer t(ctx, &last, K_RC, r); launch_rc_encode(grp, r); }
     }
     cudaEvent_t ev_rc = get_event(ctx);
     CK(cudaEventRecord(ev_rc, r));

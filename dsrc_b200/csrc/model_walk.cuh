@@ -39,7 +39,11 @@ __device__ __forceinline__ bool walk_takes(const BlockState& st, u32 order, Mode
     return cfg.alpha == 16 && st.q_count <= 5 && st.q_total > 0 && st.q_total < (1u << 22) && st.min_len == st.max_len && st.max_len >= 32 && st.max_len <= 1024;
 }
 
+#ifdef WALK_MAXNREG
+__global__ void __maxnreg__(WALK_MAXNREG) k_model_walk(Workspace ws)
+#else
 __global__ void __launch_bounds__(WALK_CTA, 2) k_model_walk(Workspace ws)
+#endif
 {
     extern __shared__ __align__(16) u8 walk_smem[];
     WalkShared& S = *(WalkShared*)walk_smem;

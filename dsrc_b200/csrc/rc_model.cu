@@ -621,6 +621,9 @@ __global__ void __maxnreg__(MODEL_REGS) k_model(Workspace ws, u64 arena_stride)
 // and, for quality, the 256-bit symbol mask of TTranslationalQualityEncoder::Store (QualityEncoder.h:332-342).
 // ------------------------------------------------------------------------------------------------
 #define RC_CTA 64
+#ifndef RC_SMEM_RING
+#define RC_SMEM_RING 1                        // 1: the chains' triples travel through a cp.async ring in shared memory; 0: straight from L2 into registers
+#endif
 #ifndef RC_L2HINT
 #define RC_L2HINT 0
 #endif
@@ -713,6 +716,7 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_qu
         while (range <= 0x00FFFFFFu) RC_RENORM();                        /* a second byte in one step is rare */ \
     } while (0)
 #define RC_RCP(hi_) __ldg(&g_rcp_lut[(hi_)])      /* hi word of a triple the model kernels wrote = tot < 2^16 */
+#if RC_SMEM_RING
     __shared__ __align__(16) ulonglong2 ring[RC_RING][2][RC_CTA];       // [slot][half][thread]: conflict-free 16-byte cells
     constexpr u32 SLOT = 2 * RC_CTA * 16, HALF = RC_CTA * 16;          // bytes per ring slot / per half slot
     const u32 rb = (u32)__cvta_generic_to_shared(&ring[0][0][threadIdx.x]);
@@ -750,6 +754,41 @@ __global__ void __launch_bounds__(RC_CTA, 16) k_rc_encode(RcGroup grp, u32 do_qu
     }
     if (pos > pos_limit) { asm volatile("cp.async.wait_all;" ::: "memory"); st.status = ST_OVERFLOW; return; }
 #undef RC_FETCH
+#else
+    // Variant without shared memory (measured, not the default): the chain's triples come straight from L2 into registers TWO sectors
+    // ahead, the reciprocals of a sector's totals one sector ahead, the chain's lines are pulled from DRAM into L2 RC_AHEAD sectors
+    // ahead. It was built on the theory that the 42 KiB of ring per SM keep the walk engines' 100 KiB CTAs of the next batch off the
+    // SMs while the chains run. Alone it is as fast as the ring (10.2 vs 10.8 ms per launch), inside the pipeline it is slower
+    // (251 vs 229 ms per 18.6 GB step), whatever the walk kernels' register count or the chains' carveout: what the chains cost the
+    // other batches' kernels is DRAM time -- a launch streams 27 GB of triples in 10 ms beside the model kernels' 14 GB of triple
+    // writes per batch -- not SM resources.
+    constexpr u32 RC_AHEAD = 24;
+    auto ld_sector = [&](u32 g, uint4& a, uint4& b) {
+        if (g < G) {
+            const uint4* p = (const uint4*)(trip + 2 * g);
+            asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+            asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p + 1));
+        }
+    };
+    for (u32 g = 0; g < RC_AHEAD && g < G; g += 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(trip + 2 * g));
+    u32 mn0 = 0, mn1 = 0, mn2 = 0, mn3 = 0;
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, f0 = n0, f1 = n0;      // sectors g+1 (n) and g+2 (f) in registers
+    ld_sector(0, n0, n1); ld_sector(1, f0, f1);
+    if (G) { mn0 = RC_RCP(n0.y); mn1 = RC_RCP(n0.w); mn2 = RC_RCP(n1.y); mn3 = RC_RCP(n1.w); }
+    for (u32 g0 = 0; g0 < G && pos <= pos_limit; g0 += RC_CHECK) {
+    const u32 g1 = min(G, g0 + RC_CHECK);
+    for (u32 g = g0; g < g1; ++g) {
+        const uint4 c0 = n0, c1 = n1;
+        const u32 m0 = mn0, m1 = mn1, m2 = mn2, m3 = mn3;
+        n0 = f0; n1 = f1;                                              // sector g+1 (loaded two sectors ago) and the reciprocals of its totals
+        if (g + 1 < G) { mn0 = RC_RCP(n0.y); mn1 = RC_RCP(n0.w); mn2 = RC_RCP(n1.y); mn3 = RC_RCP(n1.w); }
+        ld_sector(g + 2, f0, f1);
+        if ((g & 3u) == 0 && g + RC_AHEAD < G) asm volatile("prefetch.global.L2 [%0];" :: "l"(trip + 2 * (g + RC_AHEAD)));
+        RC_STEP(c0.x, c0.y, m0); RC_STEP(c0.z, c0.w, m1); RC_STEP(c1.x, c1.y, m2); RC_STEP(c1.z, c1.w, m3);
+    }
+    }
+    if (pos > pos_limit) { st.status = ST_OVERFLOW; return; }
+#endif
     for (u32 i = G * 4; i < M; ++i) { const uint2 tr = ((const uint2*)trip)[i]; const u32 m = RC_RCP(tr.y); RC_STEP(tr.x, tr.y, m); }   // <= 3 steps: < 24 bytes
     for (int k = 0; k < 8; ++k) { RC_PUT_TOP(); low <<= 8; }
     {
@@ -805,5 +844,10 @@ void launch_rc_encode(const RcGroup& grp, cudaStream_t s)
     if (!grp.n || (!dq && !dd)) return;
     u32 threads = 0;
     for (u32 g = 0; g < grp.n; ++g) threads += grp.ws[g].n_blocks * (dq + dd);
+    // developer switch DSRCGPU_RC_CARVEOUT=1: the chains ask for the largest shared-memory carveout (measured: no gain with the ring, a loss
+    // without it)
+    static int carve = -1;
+    if (carve < 0) { const char* e = getenv("DSRCGPU_RC_CARVEOUT"); carve = e ? atoi(e) : 0; }
+    if (carve) cudaFuncSetAttribute(k_rc_encode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     k_rc_encode<<<(threads + RC_CTA - 1) / RC_CTA, RC_CTA, 0, s>>>(grp, dq, dd);
 }
