@@ -53,6 +53,7 @@ struct TagShared {
     FieldD f[TAG_MAX_FIELDS];
     u32 scan[DSRC_WARPS + 1];
     u32 hist[TAG_NUM_HUF];
+    u32 t0w[64];                                  // P2: the template field of the pass, as words
     u32 nf, mixed, min_title, max_title, status;
     u32 carry, carry2, n_text_slots, n_num_slots;
     u32 hdr_bytes;
@@ -141,7 +142,7 @@ __device__ __forceinline__ u32 text_slot(const FieldD& F, u32 j)
     return s + __popc(F.need[j >> 5] & ((1u << (j & 31)) - 1));
 }
 
-__global__ void __launch_bounds__(DSRC_CTA) k_tags(Workspace ws)
+__global__ void __launch_bounds__(DSRC_CTA, 4) k_tags(Workspace ws)
 {
     __shared__ TagShared S;
     TagPool* pool = (TagPool*)(ws.tagpool + (u64)blockIdx.x * ws.tagpool_stride);
@@ -201,12 +202,33 @@ __global__ void __launch_bounds__(DSRC_CTA) k_tags(Workspace ws)
                 const u8* t = b + R.title_off[rb + r]; const u32 tl = R.title_len[rb + r];
                 mn = min(mn, tl); mx = max(mx, tl);
                 if (tl > 4095) { toolong = 1; continue; }
+                // one pass over the title, four bytes per (aligned) load -- a byte load per lane touches 32 different lines per
+                // instruction -- with the field's number parsed on the way (is_num, utils.h:163: the value of the leading digits; a
+                // number iff all digits and no leading zero)
                 u32 c = 0, start = 0, k;
+                const u32 al = (u32)((uintptr_t)t & 3u);
+                const u32* wp = (const u32*)(t - al);
+                u32 wcur = *wp >> (8 * al), wleft = 4 - al;
+                u32 v = 0, first = 0; bool digits = true;
+                u32 sep = S.f[0].sep;
                 for (k = 0; k <= tl && c < nf; ++k) {
-                    if (k < tl && t[k] != S.f[c].sep) continue;
-                    u32 v; bool isn = tag_parse_num(t + start, k - start, &v);
-                    ftab[(u64)c * fcap + r] = FE_MAKE(v, start, k - start, isn ? 1 : 0);
+                    u32 ch = 0;
+                    if (k < tl) {
+                        ch = wcur & 255u; wcur >>= 8;
+                        if (--wleft == 0) { wcur = *++wp; wleft = 4; }       // (the word after the title's last byte is inside the block: the read follows)
+                        if (k == start) first = ch;
+                        if (ch != sep) {
+                            if (digits) { if (ch >= '0' && ch <= '9') v = v * 10 + (ch - '0'); else digits = false; }
+                            continue;
+                        }
+                    }
+                    const u32 len = k - start;
+                    if (len == 0) first = t[start];                          // is_num looks at s[0] whatever the length
+                    const bool isn = digits && (len == 1 || first != '0');
+                    ftab[(u64)c * fcap + r] = FE_MAKE(v, start, len, isn ? 1 : 0);
                     start = k + 1; ++c;
+                    v = 0; digits = true;
+                    if (c < nf) sep = S.f[c].sep;
                 }
                 if (c != nf || k != tl + 1) mixed = 1;
             }
@@ -303,13 +325,41 @@ __global__ void __launch_bounds__(DSRC_CTA) k_tags(Workspace ws)
             u32 mnl = 0xFFFFFFFFu, mxl = 0, neq = 0, lenneq = 0, nonnum = 0;
             i32 mnv = 0x7FFFFFFF, mxv = (i32)0x80000000, mnd = 0x7FFFFFFF, mxd = (i32)0x80000000;
             u32 hamclr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            // the template field as words in shared memory (zero beyond its end): records are compared with it four bytes at a time
+            __syncthreads();                             // (the previous field's comparisons are done)
+            for (u32 i = tid; i < 64; i += DSRC_CTA) {
+                u32 wv = 0;
+                for (u32 j = 0; j < 4; ++j) if (4 * i + j < len0) wv |= (u32)t0[4 * i + j] << (8 * j);
+                S.t0w[i] = wv;
+            }
+            __syncthreads();
             for (u32 r = tid; r < n_rec; r += DSRC_CTA) {
                 const u64 e = col[r];
                 const u32 len = FE_LEN(e); const u8* t = b + R.title_off[rb + r] + FE_START(e);
                 mnl = min(mnl, len); mxl = max(mxl, len);
                 if (len != len0) { lenneq = 1; neq = 1; }
                 const u32 cmp = min(min(len, len0), 256u);
-                for (u32 p = 0; p < cmp; ++p) if (t[p] != t0[p]) { hamclr[p >> 5] |= 1u << (p & 31); neq = 1; }
+                if (cmp) {
+                    const u32 al = (u32)((uintptr_t)t & 3u);
+                    const u32* wp = (const u32*)(t - al);
+                    u32 lo = wp[0];
+#pragma unroll
+                    for (int hk = 0; hk < 8; ++hk) {
+                        if (32u * hk >= cmp) break;
+                        u32 acc = 0;
+                        for (u32 p = 32u * hk; p < cmp && p < 32u * hk + 32u; p += 4) {
+                            const u32 hi = wp[(p >> 2) + 1];                 // (at most 4 bytes beyond the field: inside the block)
+                            u32 dwd = __funnelshift_r(lo, hi, 8 * al) ^ S.t0w[p >> 2];
+                            lo = hi;
+                            if (cmp - p < 4) dwd &= (1u << (8 * (cmp - p))) - 1;
+                            if (dwd) {
+                                const u32 m = (((dwd & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dwd) & 0x80808080u;      // 0x80 in every differing byte
+                                acc |= (((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u)) << (p & 31u);
+                            }
+                        }
+                        if (acc) { hamclr[hk] |= acc; neq = 1; }
+                    }
+                }
                 if (!FE_ISNUM(e)) nonnum = 1;
                 const i32 v = (i32)FE_VAL(e);
                 mnv = min(mnv, v); mxv = max(mxv, v);

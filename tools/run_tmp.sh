@@ -1,5 +1,4 @@
-for v in stock rcring walk48; do
-  if [ $v = stock ]; then unset DSRC_B200_LIB; else export DSRC_B200_LIB=$PWD/build_variants/libdsrc_$v.so; fi
-  for c in 1 0; do echo "== $v carve=$c"; DSRCGPU_RC_CARVEOUT=$c python tools/phase_prof.py 50000000 0 8192 2>&1 | grep -E "call|model_quality|rc_"; done
-done
-unset DSRC_B200_LIB
+python -m pytest tests/test_gpu_parity.py tests/test_fuzz.py tests/test_gpu_archive.py -m gpu -x -q 2>&1 | tail -3
+bash tools/ab.sh 0 stock 2>&1 | grep -E "==|call|tags"
+bash tools/ab.sh 2 stock 2>&1 | grep -E "==|call|tags"
+python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --no-decode --no-serial --no-extras > gpurun_out/sw_tg.json 2> gpurun_out/sw_tg.err; python -c "import json;d=json.load(open('gpurun_out/sw_tg.json'));print(round(d['value']),{k:round(v) for k,v in d['roofline']['kernel_ms_per_step'].items()})"
