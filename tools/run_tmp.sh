@@ -1,4 +1,7 @@
 python -m pytest tests/test_gpu_parity.py tests/test_fuzz.py tests/test_gpu_archive.py -m gpu -x -q 2>&1 | tail -3
-bash tools/ab.sh 0 stock 2>&1 | grep -E "==|call|tags"
-bash tools/ab.sh 2 stock 2>&1 | grep -E "==|call|tags"
-python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --no-decode --no-serial --no-extras > gpurun_out/sw_tg.json 2> gpurun_out/sw_tg.err; python -c "import json;d=json.load(open('gpurun_out/sw_tg.json'));print(round(d['value']),{k:round(v) for k,v in d['roofline']['kernel_ms_per_step'].items()})"
+for v in stock trip8; do
+  if [ $v = stock ]; then unset DSRC_B200_LIB; else export DSRC_B200_LIB=$PWD/build_variants/libdsrc_$v.so; fi
+  echo "== $v"; python tools/phase_prof.py 50000000 0 8192 2>&1 | grep -E "call|model_|rc_"
+  DSRCGPU_SLOTS=1 python tools/phase_prof.py 6000000 0 8192 2>&1 | grep -E "model_|rc_"
+done
+unset DSRC_B200_LIB
