@@ -83,13 +83,15 @@ __global__ void __launch_bounds__(WALK_CTA, 2) k_model_walk(Workspace ws)
         const u32 sb = w < P ? (w * L + P - 1) / P : 0u, nb = w < P ? ((w + 1) * L + P - 1) / P - sb : 0u;
         const u32 magic_nb = nb ? 0xFFFFFFFFu / nb + 1u : 0u, magic_L = 0xFFFFFFFFu / L + 1u;   // x / nb = umulhi(x, magic) for x < 2^20
         u64* const tab = S.tab[w]; u16* const tab4 = S.tab4[w];
+        // the chunk's symbols are fetched one chunk ahead (the load would otherwise be exposed behind the barrier of every chunk)
+        u64 ncur = 8 * tid < M ? *(const u64*)(q + 8 * tid) : 0ull, nprv = (tid && 8 * tid < M) ? *(const u64*)(q + 8 * tid - 8) : 0ull;
         for (u32 c0 = 0; c0 < M; c0 += WALK_CHUNK) {
             __syncthreads();                              // the previous chunk's picks are done (and, first time, the tables are set)
             {   // ---- contexts of 8 consecutive symbols per thread (FetchQ::tile8x with radix-Q hash slots)
                 const u32 i = c0 + 8 * tid;
+                const u64 cur = ncur, prv = nprv;
+                if (i + WALK_CHUNK < M) { ncur = *(const u64*)(q + i + WALK_CHUNK); nprv = *(const u64*)(q + i + WALK_CHUNK - 8); }   // the arena has slack behind M
                 if (i < M) {
-                    const u64 cur = *(const u64*)(q + i);            // the arena has slack behind M
-                    const u64 prv = i ? *(const u64*)(q + i - 8) : 0ull;
                     u32 r[13];
 #pragma unroll
                     for (int k = 0; k < 5; ++k) r[k] = i ? (u32)S.rank[(u32)(prv >> (8 * (3 + k))) & 255u] : 0u;

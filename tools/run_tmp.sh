@@ -1,5 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu --no-extras > gpurun_out/bench_r2_n2.json 2> gpurun_out/bench_r2_n2.err; tail -c 300 gpurun_out/bench_r2_n2.err; python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/bench_r2_n2.json') if l.startswith('{')][-1])
-print(d['n_gpus'], d['value'], d['e2e']['value'], d['decode']['value'], d['decode']['e2e']['value'], d.get('archive',{}).get('archives_identical'))
-"
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+bash tools/ab.sh 0 stock 2>&1 | grep -E "==|call|model_quality"
+python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --no-decode --no-serial --no-extras > gpurun_out/sw_qw.json 2> gpurun_out/sw_qw.err; python -c "import json;d=json.load(open('gpurun_out/sw_qw.json'));print(round(d['value']),{k:round(v) for k,v in d['roofline']['kernel_ms_per_step'].items()})"
