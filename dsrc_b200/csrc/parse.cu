@@ -325,6 +325,9 @@ __device__ __forceinline__ u32 nz_bytes(u32 x) { return (((x & 0x7F7F7F7Fu) + 0x
 // so they leave as aligned 8-byte stores too. Of the per-record arrays only qcat_off is filled: dcat_off, dna_len and trunc_len
 // are never needed for these blocks (their users are the -q0 coders).
 #define FLAT_SYMS (DSRC_CTA * 8)
+#ifndef FLAT_PF
+#define FLAT_PF 3                                    // rounds the L2 prefetch runs ahead
+#endif
 __device__ __forceinline__ u64 flat_load8(const u8* b, u32 off, u32 in_len)
 {
     if (off + 16 <= in_len) {                          // two aligned words hold the 8 bytes
@@ -396,7 +399,13 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_preprocess_flat(Workspace ws)
     };
     u64 nxs, nxq; u32 noff;
     fetch(8 * tid, nxs, nxq, noff);
+    // the block's bytes are consumed front to back, in_len / rounds per round: the lines of the round after next but one are pulled into L2
+    const u32 rounds = (q_total + FLAT_SYMS - 1) / FLAT_SYMS, per_round = d.in_len / rounds + 1;
     for (u32 c0 = 0, it = 0; c0 < q_total; c0 += FLAT_SYMS, ++it) {
+        {
+            const u32 o = (it + FLAT_PF) * per_round + 128 * tid;
+            if (128 * tid < per_round + 128 && o < d.in_len) asm volatile("prefetch.global.L2 [%0];" :: "l"(b + o));
+        }
         const u32 p0 = c0 + 8 * tid;
         const u32 n = p0 < q_total ? min(8u, q_total - p0) : 0u;
         u64 q8 = 0, k8 = 0; u32 kept = 0;
