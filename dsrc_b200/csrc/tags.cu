@@ -163,6 +163,12 @@ __global__ void __launch_bounds__(DSRC_CTA, 4) k_tags(Workspace ws)
         const u32 len_bits = dsrc_bit_length((u64)(st.max_len - st.min_len));
         const u32 min_qlen = st.min_len;
 
+        // the titles' lines on their way into L2 while thread 0 builds the template (the batch's input has left L2 since preprocessing)
+        for (u32 r = tid; r < n_rec; r += DSRC_CTA) {
+            const u8* t = b + R.title_off[rb + r];
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(t));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(t + R.title_len[rb + r]));
+        }
         // ---- P0: field template from record 0 (InitializeFieldsStats, TagModeler.cpp:159-224)
         if (tid == 0) {
             const u8* t = b + R.title_off[rb]; const u32 tl = R.title_len[rb];
