@@ -1,3 +1,3 @@
-python bench.py > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err; tail -c 200 gpurun_out/bench_r2_final.err
-DSRCGPU_SLOTS=1 timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_model_walk|k_dna_walk|k_rc_encode|k_preprocess_flat|k_tags" --launch-skip 20 -c 5 -f -o gpurun_out/r02_full python tools/phase_prof.py 6000000 0 8192 2>&1 | tail -1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extras --no-decode --no-e2e --no-serial > gpurun_out/r02_bench_under_ncu.json 2> gpurun_out/r02_bench_under_ncu.err
+python -m pytest tests/test_gpu_parity.py tests/test_fuzz.py -m gpu -x -q 2>&1 | tail -1
+bash tools/ab.sh 0 stock 2>&1 | grep -E "==|call|model_dna"
+python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e --no-decode --no-serial --no-extras > gpurun_out/sw_d64.json 2> gpurun_out/sw_d64.err; python -c "import json;d=json.load(open('gpurun_out/sw_d64.json'));print(round(d['value']),{k:round(v) for k,v in d['roofline']['kernel_ms_per_step'].items()})"
