@@ -100,6 +100,7 @@ struct dsrcgpu_ctx {
     bool host_call = false;                          // the call in progress takes host buffers: small transfers go by kernel over mapped memory
     bool last_overflow = false;                      // the last call failed with ST_OVERFLOW
     bool wide_streams = false;                       // range-coder stream arenas at 3 bytes per symbol (set after a chain ran out of its 1.25)
+    int rc_group_host = 1;                           // the same for host-buffer calls (DSRCGPU_RC_GROUP_HOST)
     int rc_group = 2;                                // batches whose range-coder chains share one launch (<= n_slots, RC_GROUP_MAX)
     int p_serial = 2;                                // where a batch waits for the previous batch's parallel stage: 0 nowhere, 1 before parse, 2 before the model kernels
 };
@@ -168,6 +169,8 @@ extern "C" int dsrcgpu_create(dsrcgpu_ctx** out, int device, const dsrcgpu_datas
     if (const char* e = getenv("DSRCGPU_NARROW_STREAMS")) ctx->narrow_div = (u32)std::max(0, atoi(e));
     if (const char* e = getenv("DSRCGPU_RC_GROUP")) ctx->rc_group = atoi(e);
     ctx->rc_group = std::max(1, std::min(ctx->rc_group, std::min((int)RC_GROUP_MAX, std::max(1, ctx->n_slots - 1))));
+    if (const char* e = getenv("DSRCGPU_RC_GROUP_HOST")) ctx->rc_group_host = atoi(e);
+    ctx->rc_group_host = std::max(1, std::min(ctx->rc_group_host, std::min((int)RC_GROUP_MAX, std::max(1, ctx->n_slots - 1))));
     // The model launches of successive batches run one after another (DSRCGPU_PSERIAL=2: two model launches side by side only stretch
     // each other), the serial stage of a batch -- latency-bound range-coder chains at ~5 % occupancy -- runs beside the next batch's
     // parallel stage. DSRCGPU_RSTREAM=1 moves the serial stage to a high-priority stream of its own (developer switch).
@@ -478,7 +481,10 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     // batch's coding after the last byte has arrived: cutting the last batch into 2-4 parts (DSRCGPU_TAIL_SPLIT) does not end the call
     // sooner -- the range-coder chains take ~10 ms whatever the batch size and the parts wait for slots.)
     std::vector<u32> bfirst;
-    for (u32 pos = 0; pos < n; pos += ctx->max_inflight) bfirst.push_back(pos);
+    // host buffers: half-size batches (measured 47.6 -> 49.7 GB/s end to end: the input link is the bound there, and with 1 GiB batches
+    // the call ends sooner after the last byte has arrived; resident input prefers the full size, 91 vs 77 GB/s)
+    const u32 per_batch = on_device ? ctx->max_inflight : std::max(1u, ctx->max_inflight / 2);
+    for (u32 pos = 0; pos < n; pos += per_batch) bfirst.push_back(pos);
     if (!on_device && bfirst.size() >= 2) {
         const u32 a = bfirst.back(), len = n - a;
         u32 parts = 1;
@@ -635,7 +641,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
         if (rc) break;
         group[n_group++] = &sl;
         // (host buffers: the input link is the bound, not the GPU -- every batch finishes on its own, which frees its slot sooner)
-        if ((int)n_group >= (on_device ? ctx->rc_group : 1) || b + 1 == nb) { rc = close_group(); if (rc) break; }
+        if ((int)n_group >= (on_device ? ctx->rc_group : ctx->rc_group_host) || b + 1 == nb) { rc = close_group(); if (rc) break; }
         // keep S-1 batches queued behind the one the host waits for
         while (rc == DSRCGPU_OK && retired + (u32)(S - 1) <= b && S > 1 && retired < b) rc = retire(retired++);
     }

@@ -1,7 +1,2 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/r02_pytest_gpu_final.log; cat gpurun_out/r02_pytest_gpu_final.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err; tail -c 200 gpurun_out/bench_r2_final.err; python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/bench_r2_final.json') if l.startswith('{')][-1])
-print(d['value'], d['e2e']['value'], d['decode']['value'], d['decode']['e2e']['value'], d['roofline']['kernel'], d['roofline']['frac'])
-"
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_archive.py tests/test_gpu_shim.py -m gpu -x -q 2>&1 | tail -1
+python bench.py --steps 2 --warmup 2 --no-cpu --no-decode --no-serial --no-extras > gpurun_out/sw_h.json 2> gpurun_out/sw_h.err; python -c "import json;d=json.load(open('gpurun_out/sw_h.json'));print(round(d['value']),round(d['e2e']['value']),d['e2e']['frac_of_copy_ceiling'])"
