@@ -18,14 +18,17 @@
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DSRCGPU_E_CUDA; } } while (0)
 
+static unsigned long long g_devbuf_allocs = 0;       // device allocations made so far (a call that allocated says nothing about steady-state timing)
+static thread_local unsigned t_alloc_scale = 1;      // a host-buffer call with half-size batches allocates for full-size ones: a later switch does not reallocate
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        ++g_devbuf_allocs;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes * t_alloc_scale + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -97,6 +100,7 @@ struct dsrcgpu_ctx {
     cudaEvent_t call_a = nullptr, call_b = nullptr; float call_ms = 0;
     bool profiling = true, phase_prof = false;
     u32 narrow_div = 0;                              // test switch DSRCGPU_NARROW_STREAMS=<d>: narrow arenas of 1/d byte per symbol (forces the retry)
+    bool host_full = false;                          // host-buffer calls use full-size batches (the last one was bound by the coding, not by the link)
     bool host_call = false;                          // the call in progress takes host buffers: small transfers go by kernel over mapped memory
     bool last_overflow = false;                      // the last call failed with ST_OVERFLOW
     bool wide_streams = false;                       // range-coder stream arenas at 3 bytes per symbol (set after a chain ran out of its 1.25)
@@ -471,6 +475,7 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     memset(ctx->k_ms, 0, sizeof(ctx->k_ms)); memset(ctx->k_launches, 0, sizeof(ctx->k_launches));
     if (!ctx->call_a) { cudaEventCreate(&ctx->call_a); cudaEventCreate(&ctx->call_b); }
     const int S = ctx->n_slots;
+    const unsigned long long allocs_before = g_devbuf_allocs;
     ctx->host_call = !on_device;
     cudaEventRecord(ctx->call_a, ctx->slots[0].stream);
     if (on_device) {
@@ -481,9 +486,13 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     // batch's coding after the last byte has arrived: cutting the last batch into 2-4 parts (DSRCGPU_TAIL_SPLIT) does not end the call
     // sooner -- the range-coder chains take ~10 ms whatever the batch size and the parts wait for slots.)
     std::vector<u32> bfirst;
-    // host buffers: half-size batches (measured 47.6 -> 49.7 GB/s end to end: the input link is the bound there, and with 1 GiB batches
-    // the call ends sooner after the last byte has arrived; resident input prefers the full size, 91 vs 77 GB/s)
-    const u32 per_batch = on_device ? ctx->max_inflight : std::max(1u, ctx->max_inflight / 2);
+    // host buffers: half-size batches while the input link is the bound (measured 47.6 -> 49.7 GB/s end to end: with 1 GiB batches the
+    // call ends sooner after the last byte has arrived; resident input prefers the full size, 91 vs 77 GB/s). A context whose last
+    // host-buffer call was bound by the coding instead (41-level qualities: 36 GB/s of coding against 52 GB/s of link) goes back to
+    // full-size batches, which cost fewer range-coder launches (host_full, decided at the end of every call from the copy timers).
+    const u32 per_batch = (on_device || ctx->host_full) ? ctx->max_inflight : std::max(1u, ctx->max_inflight / 2);
+    struct ScaleGuard { unsigned old; ScaleGuard(unsigned v) : old(t_alloc_scale) { t_alloc_scale = v; } ~ScaleGuard() { t_alloc_scale = old; } }
+        scale_guard((!on_device && !ctx->host_full && n > per_batch) ? 2u : 1u);
     for (u32 pos = 0; pos < n; pos += per_batch) bfirst.push_back(pos);
     if (!on_device && bfirst.size() >= 2) {
         const u32 a = bfirst.back(), len = n - a;
@@ -661,6 +670,8 @@ static int encode_impl(dsrcgpu_ctx* ctx, const u8* fastq, bool on_device, const 
     CK(cudaEventSynchronize(ctx->call_b));
     cudaEventElapsedTime(&ctx->call_ms, ctx->call_a, ctx->call_b);
     collect_copy_times(ctx);
+    if (!on_device && ctx->profiling && nb >= 4 && ctx->k_ms[K_H2D] > 0 && g_devbuf_allocs == allocs_before)      // (a warm call)
+        ctx->host_full = ctx->call_ms > 1.25f * ctx->k_ms[K_H2D];
     return DSRCGPU_OK;
 }
 
