@@ -327,6 +327,8 @@ def serialized_pass(L, _lib, local_rank, ds, cs, inflight, sh, d_out, out_cap, s
     if rc1 == 0 and bool((ssz == sizes).all()):
         kser = kernel_times(L, ctx1)
         kser["_step_ms"] = (float(L.dsrcgpu_last_call_ms(ctx1)), 1)
+    else:
+        sys.stderr.write("bench.py: serialized pass skipped (rc %d: %s; sizes equal: %s)\n" % (rc1, L.dsrcgpu_last_error(ctx1).decode(), bool((ssz == sizes).all())))
     L.dsrcgpu_destroy(ctx1)
     return kser
 
@@ -483,6 +485,7 @@ def run_workload(L, _lib, torch, dist, args, rank, local_rank, world, name, prof
                       "output_identical_to_resident_leg": same}
         del h_in, h_out
     if do_serial:
+        L.dsrcgpu_release_workspace(ctx)      # room for the single-slot context of the serialized pass (each context has its own table pool)
         kser = serialized_pass(L, _lib, local_rank, ds, cs, args.inflight, sh, d_out, out_cap, sizes)
         if kser:
             peak, peak_kind = load_peaks()
