@@ -30,7 +30,12 @@ struct DevBuf {
         p = nullptr; cap = 0;
         size_t want = bytes * t_alloc_scale + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
+        if (e != cudaSuccess && t_alloc_scale > 1) {           // the head-room is a convenience, not a requirement
+            cudaGetLastError();
+            want = bytes + bytes / 8 + 256;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
