@@ -343,7 +343,10 @@ __device__ __forceinline__ u64 flat_load8(const u8* b, u32 off, u32 in_len)
     for (u32 j = 0; j < 8 && off + j < in_len; ++j) v |= (u64)b[off + j] << (8 * j);
     return v;
 }
-__global__ void __launch_bounds__(DSRC_CTA, 4) k_preprocess_flat(Workspace ws)
+#ifndef FLAT_MINB
+#define FLAT_MINB 4
+#endif
+__global__ void __launch_bounds__(DSRC_CTA, FLAT_MINB) k_preprocess_flat(Workspace ws)
 {
     const BlockDesc& d = ws.desc[blockIdx.x];
     BlockState& st = ws.state[blockIdx.x];
