@@ -72,6 +72,10 @@ def small_cases():
     c.append(("walk_len37_hot_d6_q2", synth.skewed(9000, length=37, seed=118), 6, 2, 0))
     c.append(("walk_len101_d3_q2", synth.skewed(4000, length=101, seed=119, p_major=0.6), 3, 2, 0))
     c.append(("walk_len31_d6_q2", synth.skewed(4000, length=31, seed=120, p_major=0.8), 6, 2, 0))
+    # read IDs of other platforms and archives (the tag tokenizer's envelope: field counts, title lengths, text fields)
+    for style in ("sra", "ont", "pacbio", "bgi"):
+        c.append(("ids_%s_d6_q2" % style, synth.read_id_styles(style), 6, 2, 0))
+    c.append(("ids_ont_d0_q0", synth.read_id_styles("ont", seed=52), 0, 0, 0))
     c.append(("walk_homopolymer_d6_q1", synth.skewed(3000, length=150, seed=121, p_major=0.995, levels=(2, 37)), 6, 1, 0))
     return c
 

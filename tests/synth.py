@@ -218,3 +218,33 @@ def block_scale(n_reads=1000, length=150, n_levels=41, sticky=False, seed=1, low
         ln = int(lens[i])
         out.append(b"@B.%d %d:%d\n" % (i + 1, x[i], 7 * i) + seq[i, :ln].tobytes() + b"\n+\n" + qual[i, :ln].tobytes() + b"\n")
     return b"".join(out)
+
+
+def read_id_styles(style, n_reads=600, seed=51):
+    """read IDs as other platforms / archives write them (the tag tokenizer's envelope): `sra` = SRA dumps
+    ("@SRR1770413.17 HWI-ST1106:...:1101:1249:2062 length=100"), `ont` = Nanopore (UUID, runid hash, key=value pairs, ISO time stamp:
+    ~40 separator-delimited fields, 240-byte titles), `pacbio` = "@m64011_190830_220126/4194376/ccs", `bgi` = "@V350012345L1C001R0010000001/1"."""
+    rng = np.random.default_rng(seed)
+    hexd = np.frombuffer(b"0123456789abcdef", dtype=np.uint8)
+    lines = []
+    for i in range(n_reads):
+        if style == "sra":
+            L = 100
+            title = b"@SRR1770413.%d HWI-ST1106:418:D1WJWACXX:3:1101:%d:%d length=%d" % (i + 1, 1200 + int(rng.integers(0, 20000)), 2000 + 5 * i, L)
+        elif style == "ont":
+            L = int(rng.integers(200, 900))
+            u = hexd[rng.integers(0, 16, size=32)].tobytes()
+            title = (b"@%s-%s-%s-%s-%s runid=5d1f6bd2c0b1ee3ad2b5fa2ac6bdd7a2a1a0f0c3 sampleid=S1 read=%d ch=%d start_time=2021-03-%02dT%02d:%02d:%02dZ "
+                     b"flow_cell_id=FAO12345 protocol_group_id=run_7 barcode=barcode%02d"
+                     % (u[:8], u[8:12], u[12:16], u[16:20], u[20:32], 100 + 7 * i, int(rng.integers(1, 513)), 1 + i % 28, int(rng.integers(0, 24)),
+                        int(rng.integers(0, 60)), int(rng.integers(0, 60)), int(rng.integers(1, 13))))
+        elif style == "pacbio":
+            L = int(rng.integers(300, 1200))
+            title = b"@m64011_190830_220126/%d/ccs" % (4194376 + 131 * i + int(rng.integers(0, 100)))
+        else:
+            L = 100
+            title = b"@V350012345L%dC%03dR%03d%07d/1" % (1 + i % 4, 1 + (i // 40) % 8, 1 + (i // 7) % 60, i * 3 + int(rng.integers(0, 3)))
+        sq = BASES[rng.integers(0, 4, size=L)]
+        q = _markov_quals(rng, 1, L, np.array([2, 12, 23, 37], dtype=np.uint8))[0]
+        lines.append(title + b"\n" + sq.tobytes() + b"\n+\n" + (q + 33).astype(np.uint8).tobytes() + b"\n")
+    return b"".join(lines)
