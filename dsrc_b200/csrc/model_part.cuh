@@ -26,6 +26,9 @@
 #define PART_MUL 0x9E3779B1u                  // odd: key -> key * PART_MUL mod 2^key_bits is a bijection
 #define PW 256                                // elements of a warp's tile
 #define PW_SHIFT 8
+#ifndef PART_TARGET
+#define PART_TARGET 128                       // a partition holds at most about this many elements (a warp's tile takes two or three)
+#endif
 
 // One warp walks sorted[lo, hi) a row of 32 elements at a time (element = (key << SH) | position in the loaded tile).
 // main mode: lo = start of the warp's segment; a run that began before the segment is left to the long walker (queued in longs).
@@ -194,7 +197,7 @@ __device__ bool part_engine(ModelShared& MS, F f, u32 M, u32 key_bits, u32 N, u3
     // was measured 20 % SLOWER on B200: the partitions are then written in eight interleaved pieces and pass 2 waits longer for them)
     // partitions of about 100 elements (a warp's tile holds two or three), at most 2^PART_MAX_BITS of them and never more than keys
     u32 pb = key_bits > 13 ? key_bits - 10 : 3;       // a warp's counting sort has 2^10 counters: at most 10 key bits below the partition
-    while (pb < PART_MAX_BITS && pb < key_bits && (M >> pb) > 128) ++pb;
+    while (pb < PART_MAX_BITS && pb < key_bits && (M >> pb) > PART_TARGET) ++pb;
     const u32 bins = 1u << pb, lowbits = key_bits - pb;
     f.kmul = PART_MUL; f.kmask = (1u << key_bits) - 1;
 
