@@ -111,6 +111,8 @@ def main():
     rng = np.random.default_rng(seed)
     bad = 0
     for it in range(n):
+        if it and it % 100 == 0:
+            print("...", it, "cases, bad", bad, flush=True)
         data, d, q, pr, crc = rand_case(rng)
         chunk = data[:-2] if data.endswith(b"\r\n") else data[:-1]
         if data.endswith(b"\r\n"):
